@@ -1,0 +1,182 @@
+/*
+ * pvb.h -- C ABI of libpvb.so, the B200 (sm_100a) signed-distance query library.
+ *
+ * The reference (UM-ARM-Lab/pytorch_volumetric) is pure Python and has no FFI
+ * of its own; each entry point below replaces the body of one reference
+ * operator (file:line under /root/reference) and is what a binding for that
+ * operator would call.  See INTEGRATION.md for the ctypes stub a maintainer
+ * would add on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - every "const float* pts" style argument below is a DEVICE pointer unless
+ *     its comment says HOST; descriptors (pvb_sdf_desc) are HOST structs that
+ *     hold device pointers
+ *   - all launches go to the caller's stream (`stream` is a cudaStream_t
+ *     passed as void*; NULL = legacy default stream); no allocation and no
+ *     synchronisation inside query calls
+ *   - fp32, C-contiguous; points are [n,3] AoS exactly as torch stores them
+ *   - return value: 0 on success, negative pvb_status otherwise, with a
+ *     thread-local message behind pvb_last_error()
+ */
+#ifndef PVB_H
+#define PVB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVB_VERSION 100
+
+typedef enum pvb_status {
+    PVB_OK = 0,
+    PVB_ERR_INVALID = -1,   /* bad argument */
+    PVB_ERR_CUDA = -2,      /* a CUDA runtime call or launch failed */
+    PVB_ERR_CAPACITY = -3   /* caller-provided buffer too small */
+} pvb_status;
+
+/* sub-SDF kinds understood by the fused kernels */
+enum { PVB_KIND_GRID = 0, PVB_KIND_MESH = 1, PVB_KIND_SPHERE = 2 };
+
+/* pvb_sdf_desc.flags */
+enum {
+    PVB_GRID_INDEX_FP32 = 1u << 0, /* voxel index arithmetic in fp32 (range given as Python floats);
+                                      default is fp64, the dtype torch infers for numpy ranges */
+    PVB_GRID_OOB_GT     = 1u << 1, /* OutOfBoundsStrategy.LOOKUP_GT_SDF: out-of-range points take the
+                                      mesh query (mesh fields must be filled); default BOUNDING_BOX */
+    PVB_GRID_PRUNE_OK   = 1u << 2  /* table verified to satisfy val >= dist(voxel centre, bb): composed
+                                      kernels may skip lookups that provably cannot win the min */
+};
+
+/* pvb_mesh_query mode flags */
+enum {
+    PVB_MESH_SIGNED         = 1u << 0, /* ray-parity inside test + sign (sdf.py:146-157) */
+    PVB_MESH_SURFACE_NORMAL = 1u << 1, /* |d| < 1e-3 -> gradient = face normal (sdf.py:162-164) */
+    PVB_MESH_DEFAULT        = 3u
+};
+
+/*
+ * One queryable object.  224 bytes (pvb_sizeof_sdf_desc()), POD, host-resident (device pointers
+ * inside); arrays of these are copied to the device by the caller for the
+ * composed kernels.
+ *
+ * GRID part  = CachedSDF state (sdf.py:521-525): interleaved table
+ *              {val, gx, gy, gz} per voxel in C order (last axis fastest),
+ *              grid geometry, the mesh AABB used by the BOUNDING_BOX
+ *              out-of-range rule (sdf.py:555-571).
+ * MESH part  = ObjectFactory state (sdf.py:115-120): BVH4 nodes + leaf-ordered
+ *              triangles from pvb_bvh_build, fp32 face normals in ORIGINAL
+ *              face order, ray "destination" bbox(padding=1.0).max (sdf.py:147).
+ * SPHERE     = SphereSDF radius (sdf.py:285-299).
+ */
+typedef struct pvb_sdf_desc {
+    int32_t kind;
+    uint32_t flags;
+    /* ---- grid ---- */
+    const void *table;          /* device float4[n0*n1*n2] */
+    int32_t dims[3];
+    int32_t _pad0;
+    double min64[3];            /* fp64 index mode: round((double(p) - min64) / res64) */
+    double res64[3];
+    float min32[3];             /* fp32 index mode: rintf((p - min32) / res32) */
+    float res32[3];
+    float valid_lo[3];          /* inclusive fp32 bounds equivalent to all(min <= p <= max) */
+    float valid_hi[3];
+    float bb_min[3];            /* surface AABB, fp32 */
+    float bb_max[3];
+    float prune_margin;         /* see PVB_GRID_PRUNE_OK */
+    /* ---- mesh ---- */
+    int32_t n_nodes;
+    const void *nodes;          /* device pvb_bvh4_node[n_nodes] */
+    const void *tris;           /* device float4[3*n_tris] */
+    const float *face_normals;  /* device float[3*n_tris], original face order */
+    int32_t n_tris;
+    float ray_far[3];
+    uint32_t ray_seed;          /* seed of the deterministic stand-in for sdf.py:149's jitter */
+    /* ---- sphere ---- */
+    float radius;
+    uint8_t _reserved[16];
+} pvb_sdf_desc;
+
+/* BVH4 node, 128 bytes: SoA child boxes + child links.
+ * child >= 0: inner node index; child < 0 and != INT32_MIN: leaf, ~child =
+ * (first_triangle << 2) | (count - 1), count in 1..4; INT32_MIN: empty slot. */
+typedef struct pvb_bvh4_node {
+    float lox[4], loy[4], loz[4];
+    float hix[4], hiy[4], hiz[4];
+    int32_t child[4];
+    int32_t _pad[4];
+} pvb_bvh4_node;
+
+const char *pvb_last_error(void);
+int pvb_version(void);
+/* sizeof the structs above as compiled, so a binding can verify its mirror */
+int pvb_sizeof_sdf_desc(void);
+int pvb_sizeof_bvh4_node(void);
+
+/* ---- mesh preprocessing (HOST -> HOST), replaces RaycastingScene construction, sdf.py:115-118 ---- */
+int64_t pvb_bvh_max_nodes(int64_t n_faces);
+/* verts HOST float[n_verts*3], faces HOST int32[n_faces*3];
+ * nodes_out HOST pvb_bvh4_node[node_capacity]; tris_out HOST float[n_faces*12]
+ * (3 x {x,y,z,w}; w of vertex 0 carries the original face index as int bits). */
+int pvb_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, int64_t n_faces,
+                  void *nodes_out, int64_t node_capacity, float *tris_out,
+                  int64_t *n_nodes_out, int32_t *max_depth_out);
+
+/* ---- ObjectFactory._do_object_frame_closest_point, sdf.py:122-172 (MeshSDF.__call__, sdf.py:312-329) ----
+ * out_dist[n], out_grad[n*3] required; out_closest[n*3], out_face[n] (int32, original index),
+ * out_normal[n*3] optional (NULL to skip). */
+int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_t n, uint32_t mode,
+                   float *out_dist, float *out_grad, float *out_closest, int32_t *out_face,
+                   float *out_normal, void *stream);
+
+/* ---- CachedSDF.__call__ (sdf.py:535-571) and outside_surface (sdf.py:593-602) ----
+ * out_val / out_grad may be NULL when only occupancy is wanted; out_outside (uint8, 0/1)
+ * may be NULL; out_index (int64 ravelled key, -1 if out of range) may be NULL. */
+int pvb_grid_lookup(const pvb_sdf_desc *grid, const float *pts, int64_t n,
+                    float *out_val, float *out_grad, uint8_t *out_outside, float surface_level,
+                    int64_t *out_index, void *stream);
+
+/* ---- SphereSDF.__call__, sdf.py:291-295 ---- */
+int pvb_sphere_query(float radius, const float *pts, int64_t n, float *out_val, float *out_grad, void *stream);
+
+/* ---- ComposedSDF.__call__ / RobotSDF.__call__ (sdf.py:392-433, model_to_sdf.py:117-125) ----
+ * descs_dev: DEVICE array of n_sdf pvb_sdf_desc; xforms: DEVICE float[n_sdf*n_cfg][16] object->sub-frame
+ * 4x4 row-major, sub-SDF-major (sdf.py:385-390).  The winning gradient is mapped back with
+ * g_obj = g_link @ M[:3,:3]: the reference's link_frame_to_obj_frame[i].transform_normals
+ * (sdf.py:380-383, 409) is g @ inv(inv(M)[:3,:3]), and the two inversions cancel;
+ * pts DEVICE [n_pts,3]; out_val [n_cfg*n_pts], out_grad [n_cfg*n_pts*3]; out_which optional
+ * int32 argmin index.  cfg_begin/cfg_count select a contiguous slab of configurations (multi-GPU
+ * sharding); outputs are indexed relative to cfg_begin.  needs_mesh != 0 when any descriptor is a MESH or a
+ * GRID with PVB_GRID_OOB_GT (selects the instantiation that contains the tree walk). */
+int pvb_composed_query(const void *descs_dev, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
+                       int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count,
+                       const float *pts, int64_t n_pts, uint32_t mesh_mode,
+                       float *out_val, float *out_grad, int32_t *out_which, void *stream);
+
+/* ---- batch_chamfer_dist, chamfer.py:79-94 ----
+ * world_to_object DEVICE float[n_tf][16]; pts DEVICE [n_pts,3] world frame;
+ * workspace DEVICE float[n_tf * pvb_chamfer_workspace(n_pts)]; out DEVICE float[n_tf]
+ * = mean_i (scale * d_i)^2 with d the unsigned distance to `obj` (mesh) or the value of
+ * `obj` (grid / sphere). */
+int64_t pvb_chamfer_workspace(int64_t n_pts);
+int pvb_chamfer(const pvb_sdf_desc *obj, const float *world_to_object, int32_t n_tf,
+                const float *pts, int64_t n_pts, float scale, float *workspace, float *out, void *stream);
+
+/* ---- sample_mesh_points, sdf.py:650-658 (area-uniform surface samples) ----
+ * verts64 DEVICE double[n_verts*3]; faces DEVICE int32[n_faces*3]; cum_counts DEVICE int64[n_faces]
+ * inclusive cumulative sample count per face (stratified allocation);
+ * out_pts DEVICE double[n*3]; out_face DEVICE int32[n]. */
+int pvb_mesh_sample(const double *verts64, const int32_t *faces, int64_t n_faces, const int64_t *cum_counts,
+                    int64_t n, uint64_t seed, double *out_pts, int32_t *out_face, void *stream);
+
+/* ---- rigid transform helpers used by the generic (unfused) composition path ---- */
+int pvb_transform_points(const float *xforms, int32_t n_tf, const float *pts, int64_t n_pts,
+                         float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVB_H */

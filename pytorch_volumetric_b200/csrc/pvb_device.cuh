@@ -1,0 +1,359 @@
+// pvb_device.cuh -- device-side building blocks shared by the sm_100a kernels.
+//
+//   grid_eval      CachedSDF.__call__ for one point          (reference sdf.py:535-571)
+//   bvh_closest    closest point on the mesh                 (Embree rtcPointQuery role, sdf.py:134)
+//   bvh_parity     ray/triangle crossing parity              (count_intersections role, sdf.py:152-154)
+//   mesh_eval      ObjectFactory._do_object_frame_closest_point epilogue (sdf.py:139-164)
+#pragma once
+#include "../../include/pvb.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pvb {
+
+constexpr int kStack = 40;            // traversal stack entries per thread (builder bounds depth)
+#define PVB_INF __int_as_float(0x7f800000)
+
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ float sel(f3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+// The top of the BVH staged in shared memory (first `n` nodes of the BFS layout).
+struct NodeStage {
+    const float4 *smem;   // 8 float4 per node
+    int n;
+};
+
+__device__ __forceinline__ const float4 *node_ptr(const float4 *gnodes, const NodeStage &st, int idx) {
+    return idx < st.n ? st.smem + 8 * idx : gnodes + 8 * (size_t)idx;
+}
+
+// ----------------------------------------------------------------------------
+// Closest point on triangle (Ericson, RTCD 5.1.5), fp32.
+__device__ __forceinline__ f3 closest_on_triangle(f3 p, f3 a, f3 b, f3 c) {
+    const f3 ab = b - a, ac = c - a, ap = p - a;
+    const float d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= 0.f && d2 <= 0.f) return a;
+    const f3 bp = p - b;
+    const float d3 = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3 >= 0.f && d4 <= d3) return b;
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
+        const float v = __fdiv_rn(d1, d1 - d3);
+        return a + ab * v;
+    }
+    const f3 cp = p - c;
+    const float d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= 0.f && d5 <= d6) return c;
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
+        const float w = __fdiv_rn(d2, d2 - d6);
+        return a + ac * w;
+    }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+        const float w = __fdiv_rn(d4 - d3, (d4 - d3) + (d5 - d6));
+        return b + (c - b) * w;
+    }
+    const float denom = __fdiv_rn(1.f, va + vb + vc);
+    const float v = vb * denom, w = vc * denom;
+    return a + ab * v + ac * w;
+}
+
+struct Closest {
+    f3 q;        // closest point
+    float d2;    // squared distance
+    int face;    // original face index, -1 if nothing within the initial radius
+};
+
+__device__ __forceinline__ float box_d2(float lx, float ly, float lz, float hx, float hy, float hz, f3 p) {
+    const float dx = fmaxf(fmaxf(lx - p.x, p.x - hx), 0.f);
+    const float dy = fmaxf(fmaxf(ly - p.y, p.y - hy), 0.f);
+    const float dz = fmaxf(fmaxf(lz - p.z, p.z - hz), 0.f);
+    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+
+// Nearest-first BVH4 descent.  `init_d2` is an initial search radius (squared);
+// candidates farther than that are never reported (face stays -1).
+__device__ __forceinline__ Closest bvh_closest(const float4 *__restrict__ gnodes, const NodeStage &st,
+                                               const float4 *__restrict__ tris, f3 p, float init_d2) {
+    Closest best;
+    best.q = mk3(0.f, 0.f, 0.f);
+    best.d2 = init_d2;
+    best.face = -1;
+    int stack_n[kStack];
+    float stack_d[kStack];
+    int sp = 0;
+    stack_n[sp] = 0; stack_d[sp] = 0.f; ++sp;
+    // box distances are lower bounds only up to fp32 rounding of either side; keep a margin
+    constexpr float kSlack = 0.99999f;
+    while (sp > 0) {
+        --sp;
+        const int ni = stack_n[sp];
+        if (stack_d[sp] * kSlack > best.d2) continue;
+        const float4 *n = node_ptr(gnodes, st, ni);
+        const float4 lox = n[0], loy = n[1], loz = n[2], hix = n[3], hiy = n[4], hiz = n[5];
+        const int4 ch = *reinterpret_cast<const int4 *>(n + 6);
+        float d[4];
+        int c[4];
+        d[0] = box_d2(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, p); c[0] = ch.x;
+        d[1] = box_d2(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, p); c[1] = ch.y;
+        d[2] = box_d2(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, p); c[2] = ch.z;
+        d[3] = box_d2(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, p); c[3] = ch.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c[k] == INT32_MIN) d[k] = PVB_INF;
+        // sort the four children by distance (5-comparator network), nearest first
+#define PVB_CSWAP(i, j)                                                          \
+    if (d[j] < d[i]) { const float td = d[i]; d[i] = d[j]; d[j] = td;            \
+                       const int tc = c[i]; c[i] = c[j]; c[j] = tc; }
+        PVB_CSWAP(0, 1) PVB_CSWAP(2, 3) PVB_CSWAP(0, 2) PVB_CSWAP(1, 3) PVB_CSWAP(1, 2)
+#undef PVB_CSWAP
+        // leaves first (nearest first) so that the bound tightens before pushing
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c[k] < 0 && c[k] != INT32_MIN && d[k] * kSlack <= best.d2) {
+                const unsigned code = (unsigned)~c[k];
+                const int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
+                for (int t = first; t < first + cnt; ++t) {
+                    const float4 v0 = __ldg(tris + 3 * (size_t)t);
+                    const float4 v1 = __ldg(tris + 3 * (size_t)t + 1);
+                    const float4 v2 = __ldg(tris + 3 * (size_t)t + 2);
+                    const f3 q = closest_on_triangle(p, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z),
+                                                     mk3(v2.x, v2.y, v2.z));
+                    const f3 g = q - p;
+                    const float dd = dot(g, g);
+                    const int face = __float_as_int(v0.w);
+                    // ties -> lowest original face index (the oracle's brute-force rule)
+                    if (dd < best.d2 || (dd == best.d2 && (best.face < 0 || face < best.face))) {
+                        best.d2 = dd; best.q = q; best.face = face;
+                    }
+                }
+            }
+        }
+        // inner children, farthest pushed first
+#pragma unroll
+        for (int k = 3; k >= 0; --k) {
+            if (c[k] >= 0 && d[k] * kSlack <= best.d2 && sp < kStack) {
+                stack_n[sp] = c[k]; stack_d[sp] = d[k]; ++sp;
+            }
+        }
+    }
+    return best;
+}
+
+// ----------------------------------------------------------------------------
+// Crossing parity of the ray o + t*dir, t in [0, inf), with the triangle soup.
+// Watertight ray/triangle test (Woop, Benthin, Wald 2013): shared edges and
+// vertices are counted consistently, so the parity of a closed mesh is exact.
+__device__ __forceinline__ int bvh_parity(const float4 *__restrict__ gnodes, const NodeStage &st,
+                                          const float4 *__restrict__ tris, f3 o, f3 dir) {
+    // shear setup
+    const float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
+    int kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+    int kx = kz + 1; if (kx == 3) kx = 0;
+    int ky = kx + 1; if (ky == 3) ky = 0;
+    if (sel(dir, kz) < 0.f) { const int t = kx; kx = ky; ky = t; }
+    const float dz = sel(dir, kz);
+    const float Sx = __fdiv_rn(sel(dir, kx), dz), Sy = __fdiv_rn(sel(dir, ky), dz), Sz = __fdiv_rn(1.f, dz);
+    // slab setup (guard exact zeros; the box test only has to be conservative)
+    const float tiny = 1e-30f;
+    const f3 inv = mk3(__fdiv_rn(1.f, fabsf(dir.x) < tiny ? copysignf(tiny, dir.x) : dir.x),
+                       __fdiv_rn(1.f, fabsf(dir.y) < tiny ? copysignf(tiny, dir.y) : dir.y),
+                       __fdiv_rn(1.f, fabsf(dir.z) < tiny ? copysignf(tiny, dir.z) : dir.z));
+    int hits = 0;
+    int stack_n[kStack];
+    int sp = 0;
+    stack_n[sp++] = 0;
+    while (sp > 0) {
+        const int ni = stack_n[--sp];
+        const float4 *n = node_ptr(gnodes, st, ni);
+        const float4 lox = n[0], loy = n[1], loz = n[2], hix = n[3], hiy = n[4], hiz = n[5];
+        const int4 ch = *reinterpret_cast<const int4 *>(n + 6);
+        const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w},
+                    lz[4] = {loz.x, loz.y, loz.z, loz.w};
+        const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w},
+                    hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
+        const int c[4] = {ch.x, ch.y, ch.z, ch.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c[k] == INT32_MIN) continue;
+            const float t0x = (lx[k] - o.x) * inv.x, t1x = (hx[k] - o.x) * inv.x;
+            const float t0y = (ly[k] - o.y) * inv.y, t1y = (hy[k] - o.y) * inv.y;
+            const float t0z = (lz[k] - o.z) * inv.z, t1z = (hz[k] - o.z) * inv.z;
+            float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+            float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+            // conservative padding of the interval (Ize 2013)
+            tmin = tmin - fabsf(tmin) * 4e-7f;
+            tmax = tmax + fabsf(tmax) * 4e-7f;
+            if (!(fmaxf(tmin, 0.f) <= tmax)) continue;
+            if (c[k] >= 0) {
+                if (sp < kStack) stack_n[sp++] = c[k];
+                continue;
+            }
+            const unsigned code = (unsigned)~c[k];
+            const int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
+            for (int t = first; t < first + cnt; ++t) {
+                const float4 v0 = __ldg(tris + 3 * (size_t)t);
+                const float4 v1 = __ldg(tris + 3 * (size_t)t + 1);
+                const float4 v2 = __ldg(tris + 3 * (size_t)t + 2);
+                const f3 A = mk3(v0.x, v0.y, v0.z) - o, B = mk3(v1.x, v1.y, v1.z) - o,
+                         C = mk3(v2.x, v2.y, v2.z) - o;
+                const float Akz = sel(A, kz), Bkz = sel(B, kz), Ckz = sel(C, kz);
+                // sheared coordinates: a function of the vertex alone, so shared
+                // vertices get bit-identical values in every triangle
+                const float Ax = fmaf(-Sx, Akz, sel(A, kx)), Ay = fmaf(-Sy, Akz, sel(A, ky));
+                const float Bx = fmaf(-Sx, Bkz, sel(B, kx)), By = fmaf(-Sy, Bkz, sel(B, ky));
+                const float Cx = fmaf(-Sx, Ckz, sel(C, kx)), Cy = fmaf(-Sy, Ckz, sel(C, ky));
+                // edge functions without contraction: exact antisymmetry across a shared edge
+                float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+                float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+                float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+                if (U == 0.f || V == 0.f || W == 0.f) {
+                    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+                    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+                    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+                }
+                if ((U < 0.f || V < 0.f || W < 0.f) && (U > 0.f || V > 0.f || W > 0.f)) continue;
+                const float det = U + V + W;
+                if (det == 0.f) continue;
+                const float Az = Sz * Akz, Bz = Sz * Bkz, Cz = Sz * Ckz;
+                const float T = fmaf(U, Az, fmaf(V, Bz, W * Cz));
+                // t = T / det >= 0
+                if ((det > 0.f) ? (T >= 0.f) : (T <= 0.f)) ++hits;
+            }
+        }
+    }
+    return hits & 1;
+}
+
+// ----------------------------------------------------------------------------
+// Deterministic stand-in for the reference's unseeded ray jitter (sdf.py:149):
+// three ~N(0,1) numbers per point from an integer hash (sum of four 16-bit
+// uniforms), every step exact in fp32 so that a host mirror reproduces it.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ float hash_normal(uint32_t seed, uint64_t idx, uint32_t comp) {
+    const uint32_t h0 = mix32(seed ^ mix32((uint32_t)idx * 3u + comp + 0x9e3779b9u) ^ mix32((uint32_t)(idx >> 32) + 0x85ebca6bu));
+    const uint32_t h1 = mix32(h0 + 0x6a09e667u);
+    const float s = (float)((h0 & 0xffffu) + (h0 >> 16) + (h1 & 0xffffu) + (h1 >> 16));
+    return (s - 131070.0f) * 2.6428816e-05f;   // 1 / sqrt(4 * (65536^2 - 1) / 12)
+}
+
+struct SdfOut { float val; f3 grad; };
+
+// MeshSDF value + gradient for one point (sdf.py:139-164).
+//   mode: PVB_MESH_* flags.  `idx` seeds the ray jitter.
+__device__ __forceinline__ SdfOut mesh_eval(const pvb_sdf_desc &m, const NodeStage &st, f3 p, uint32_t mode,
+                                            uint64_t idx, f3 *closest_out, int *face_out) {
+    const float4 *nodes = reinterpret_cast<const float4 *>(m.nodes);
+    const float4 *tris = reinterpret_cast<const float4 *>(m.tris);
+    const Closest c = bvh_closest(nodes, st, tris, p, PVB_INF);
+    f3 g = c.q - p;                                            // sdf.py:139
+    float dist = sqrtf(fmaf(g.x, g.x, fmaf(g.y, g.y, g.z * g.z)));   // sdf.py:141
+    if (dist > 0.f) {                                          // sdf.py:143-144
+        g.x = __fdiv_rn(g.x, dist); g.y = __fdiv_rn(g.y, dist); g.z = __fdiv_rn(g.z, dist);
+    }
+    bool inside = false;
+    if (mode & PVB_MESH_SIGNED) {                              // sdf.py:146-154
+        const f3 dir = mk3(fmaf(1e-4f, hash_normal(m.ray_seed, idx, 0), m.ray_far[0]),
+                           fmaf(1e-4f, hash_normal(m.ray_seed, idx, 1), m.ray_far[1]),
+                           fmaf(1e-4f, hash_normal(m.ray_seed, idx, 2), m.ray_far[2]));
+        inside = bvh_parity(nodes, st, tris, p, dir) != 0;
+    }
+    if (inside) dist = -dist;                                  // sdf.py:155
+    else { g.x = -g.x; g.y = -g.y; g.z = -g.z; }               // sdf.py:157
+    if ((mode & PVB_MESH_SURFACE_NORMAL) && fabsf(dist) < 1e-3f && c.face >= 0) {   // sdf.py:162-164
+        const float *fn = m.face_normals + 3 * (size_t)c.face;
+        g = mk3(__ldg(fn), __ldg(fn + 1), __ldg(fn + 2));
+    }
+    if (closest_out) *closest_out = c.q;
+    if (face_out) *face_out = c.face;
+    SdfOut o; o.val = dist; o.grad = g;
+    return o;
+}
+
+// ----------------------------------------------------------------------------
+// CachedSDF: nearest-voxel index (TorchMultidimView.ensure_index_key semantics).
+// Returns the ravelled key, or -1 when the point fails all(min <= p <= max).
+__device__ __forceinline__ long long grid_key(const pvb_sdf_desc &g, f3 p) {
+    const bool inb = (p.x >= g.valid_lo[0]) & (p.x <= g.valid_hi[0]) & (p.y >= g.valid_lo[1]) &
+                     (p.y <= g.valid_hi[1]) & (p.z >= g.valid_lo[2]) & (p.z <= g.valid_hi[2]);
+    if (!inb) return -1;
+    int k[3];
+    const float pv[3] = {p.x, p.y, p.z};
+    if (g.flags & PVB_GRID_INDEX_FP32) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) k[a] = (int)rintf(__fdiv_rn(pv[a] - g.min32[a], g.res32[a]));
+    } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) k[a] = (int)rint(__ddiv_rn((double)pv[a] - g.min64[a], g.res64[a]));
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) k[a] = min(max(k[a], 0), g.dims[a] - 1);   // memory safety only
+    return ((long long)k[0] * g.dims[1] + k[1]) * g.dims[2] + k[2];
+}
+
+// Point-to-AABB rule for out-of-range points (sdf.py:555-571).
+__device__ __forceinline__ SdfOut bbox_eval(const pvb_sdf_desc &g, f3 p) {
+    float dlt[3];
+    const float pv[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float below = g.bb_min[a] - pv[a];
+        const bool on = below > 0.f;
+        below = on ? below : 0.f;
+        float above = pv[a] - g.bb_max[a];
+        above = above > 0.f ? above : 0.f;
+        const float t = below + above;
+        dlt[a] = on ? -t : t;
+    }
+    const float dist = sqrtf(dlt[0] * dlt[0] + dlt[1] * dlt[1] + dlt[2] * dlt[2]);
+    SdfOut o;
+    o.val = dist;
+    o.grad = mk3(__fdiv_rn(dlt[0], dist), __fdiv_rn(dlt[1], dist), __fdiv_rn(dlt[2], dist));
+    return o;
+}
+
+// kMesh = false compiles the tree walk out (BOUNDING_BOX-only instantiation: no stack, few registers).
+template <bool kMesh>
+__device__ __forceinline__ SdfOut grid_eval(const pvb_sdf_desc &g, const NodeStage &st, f3 p, uint32_t mesh_mode,
+                                            uint64_t idx, long long *key_out) {
+    const long long key = grid_key(g, p);
+    if (key_out) *key_out = key;
+    if (key >= 0) {
+        const float4 e = __ldg(reinterpret_cast<const float4 *>(g.table) + key);
+        SdfOut o; o.val = e.x; o.grad = mk3(e.y, e.z, e.w);
+        return o;
+    }
+    if constexpr (kMesh) {
+        if (g.flags & PVB_GRID_OOB_GT) return mesh_eval(g, st, p, mesh_mode, idx, nullptr, nullptr);   // sdf.py:553-554
+    }
+    return bbox_eval(g, p);
+}
+
+__device__ __forceinline__ SdfOut sphere_eval(float radius, f3 p) {   // sdf.py:291-295
+    const float r = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+    const float den = r + 1e-12f;
+    SdfOut o;
+    o.val = r - radius;
+    o.grad = mk3(__fdiv_rn(p.x, den), __fdiv_rn(p.y, den), __fdiv_rn(p.z, den));
+    return o;
+}
+
+// Distance from p to the surface AABB of a sub-SDF: a lower bound of its value
+// whenever p lies outside the box.
+__device__ __forceinline__ float aabb_lower_bound(const pvb_sdf_desc &g, f3 p) {
+    const float dx = fmaxf(fmaxf(g.bb_min[0] - p.x, p.x - g.bb_max[0]), 0.f);
+    const float dy = fmaxf(fmaxf(g.bb_min[1] - p.y, p.y - g.bb_max[1]), 0.f);
+    const float dz = fmaxf(fmaxf(g.bb_min[2] - p.z, p.z - g.bb_max[2]), 0.f);
+    return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+}  // namespace pvb

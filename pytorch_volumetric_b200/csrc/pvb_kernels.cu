@@ -1,0 +1,578 @@
+// pvb_kernels.cu -- sm_100a kernels and the C ABI of libpvb.so (see include/pvb.h).
+//
+// No tensor-core work anywhere on this path (there is no dense contraction);
+// the kernels are HBM-streaming (grid lookup, composed lookup) or
+// latency/L1-bound tree walks (mesh query, chamfer).
+#include "pvb_device.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+void pvb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *pvb_last_error(void) { return g_err; }
+extern "C" int pvb_version(void) { return PVB_VERSION; }
+extern "C" int pvb_sizeof_sdf_desc(void) { return (int)sizeof(pvb_sdf_desc); }
+extern "C" int pvb_sizeof_bvh4_node(void) { return (int)sizeof(pvb_bvh4_node); }
+
+static_assert(sizeof(pvb_bvh4_node) == 128, "BVH4 node must be 128 bytes");
+static_assert(sizeof(pvb_sdf_desc) % 8 == 0, "descriptor arrays must keep 8-byte alignment");
+
+#define PVB_CHECK_LAUNCH(name)                                                        \
+    do {                                                                              \
+        cudaError_t e_ = cudaGetLastError();                                          \
+        if (e_ != cudaSuccess) {                                                      \
+            pvb_set_error("%s: launch failed: %s", name, cudaGetErrorString(e_));     \
+            return PVB_ERR_CUDA;                                                      \
+        }                                                                             \
+    } while (0)
+
+namespace pvb {
+
+// ------------------------------------------------------------ device info
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ------------------------------------------- TMA bulk copy (global -> smem)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// Stage the first n_stage BVH nodes (BFS prefix = top of the tree) into shared
+// memory with one bulk asynchronous copy; every thread then waits on the mbarrier.
+__device__ __forceinline__ NodeStage stage_nodes(const void *gnodes, int n_nodes, int n_stage_max,
+                                                 unsigned char *smem_raw, uint64_t *bar) {
+    NodeStage st;
+    const int n = min(n_nodes, n_stage_max);
+    st.smem = reinterpret_cast<const float4 *>(smem_raw);
+    st.n = n;
+    if (n > 0) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)n * 128u;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smem_raw, gnodes, bytes, bar);
+        }
+        mbar_wait(bar, 0);
+    }
+    return st;
+}
+
+__device__ __forceinline__ f3 load_point(const float *__restrict__ pts, long long i) {
+    return mk3(__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2));
+}
+
+// ================================================================ mesh query
+constexpr int kMeshThreads = 256;
+
+__global__ void __launch_bounds__(kMeshThreads)
+mesh_query_kernel(const pvb_sdf_desc m, const float *__restrict__ pts, long long n, uint32_t mode, int n_stage_max,
+                  float *__restrict__ out_dist, float *__restrict__ out_grad, float *__restrict__ out_closest,
+                  int *__restrict__ out_face, float *__restrict__ out_normal) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    const NodeStage st = stage_nodes(m.nodes, m.n_nodes, n_stage_max, smem_raw, &bar);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const f3 p = load_point(pts, i);
+        f3 q;
+        int face;
+        const SdfOut o = mesh_eval(m, st, p, mode, (uint64_t)i, &q, &face);
+        out_dist[i] = o.val;
+        out_grad[3 * i] = o.grad.x; out_grad[3 * i + 1] = o.grad.y; out_grad[3 * i + 2] = o.grad.z;
+        if (out_closest) { out_closest[3 * i] = q.x; out_closest[3 * i + 1] = q.y; out_closest[3 * i + 2] = q.z; }
+        if (out_face) out_face[i] = face;
+        if (out_normal) {
+            const float *fn = m.face_normals + 3 * (size_t)max(face, 0);
+            out_normal[3 * i] = __ldg(fn); out_normal[3 * i + 1] = __ldg(fn + 1); out_normal[3 * i + 2] = __ldg(fn + 2);
+        }
+    }
+}
+
+// =============================================================== grid lookup
+// Streaming kernel: 28 B of compulsory HBM traffic per point (12 in, 16 out);
+// the table (16 B/voxel, interleaved {val,gx,gy,gz}) stays L2 resident.
+constexpr int kGridThreads = 256;
+
+// 4 points per thread: three 128-bit loads cover 4 xyz triples, results leave
+// as one float4 of values and three float4 of gradients.
+template <bool kMesh>
+__global__ void __launch_bounds__(kGridThreads)
+grid_lookup_vec4_kernel(const pvb_sdf_desc g, const float4 *__restrict__ pts4, long long n_quads, uint32_t mesh_mode,
+                        float4 *__restrict__ out_val4, float4 *__restrict__ out_grad4,
+                        uchar4 *__restrict__ out_outside4, float surface_level, longlong2 *__restrict__ out_index2) {
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_quads; t += stride) {
+        const float4 a = __ldcs(pts4 + 3 * t), b = __ldcs(pts4 + 3 * t + 1), c = __ldcs(pts4 + 3 * t + 2);
+        const f3 p[4] = {mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w)};
+        SdfOut o[4];
+        long long key[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = grid_eval<kMesh>(g, st, p[k], mesh_mode, (uint64_t)(4 * t + k), &key[k]);
+        if (out_val4) __stcs(out_val4 + t, make_float4(o[0].val, o[1].val, o[2].val, o[3].val));
+        if (out_grad4) {
+            __stcs(out_grad4 + 3 * t, make_float4(o[0].grad.x, o[0].grad.y, o[0].grad.z, o[1].grad.x));
+            __stcs(out_grad4 + 3 * t + 1, make_float4(o[1].grad.y, o[1].grad.z, o[2].grad.x, o[2].grad.y));
+            __stcs(out_grad4 + 3 * t + 2, make_float4(o[2].grad.z, o[3].grad.x, o[3].grad.y, o[3].grad.z));
+        }
+        if (out_outside4) {   // outside_surface: out of range => outside (sdf.py:600-601)
+            uchar4 m;
+            m.x = key[0] < 0 ? 1 : (o[0].val > surface_level);
+            m.y = key[1] < 0 ? 1 : (o[1].val > surface_level);
+            m.z = key[2] < 0 ? 1 : (o[2].val > surface_level);
+            m.w = key[3] < 0 ? 1 : (o[3].val > surface_level);
+            out_outside4[t] = m;
+        }
+        if (out_index2) {
+            out_index2[2 * t] = make_longlong2(key[0], key[1]);
+            out_index2[2 * t + 1] = make_longlong2(key[2], key[3]);
+        }
+    }
+}
+
+// scalar variant for the tail and for unaligned views
+template <bool kMesh>
+__global__ void __launch_bounds__(kGridThreads)
+grid_lookup_scalar_kernel(const pvb_sdf_desc g, const float *__restrict__ pts, long long first, long long n,
+                          uint32_t mesh_mode, float *__restrict__ out_val, float *__restrict__ out_grad,
+                          uint8_t *__restrict__ out_outside, float surface_level, long long *__restrict__ out_index) {
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const f3 p = load_point(pts, i);
+        long long key;
+        const SdfOut o = grid_eval<kMesh>(g, st, p, mesh_mode, (uint64_t)i, &key);
+        if (out_val) out_val[i] = o.val;
+        if (out_grad) { out_grad[3 * i] = o.grad.x; out_grad[3 * i + 1] = o.grad.y; out_grad[3 * i + 2] = o.grad.z; }
+        if (out_outside) out_outside[i] = key < 0 ? 1 : (o.val > surface_level);
+        if (out_index) out_index[i] = key;
+    }
+}
+
+// ==================================================================== sphere
+__global__ void sphere_kernel(float radius, const float *__restrict__ pts, long long n, float *__restrict__ out_val,
+                              float *__restrict__ out_grad) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const SdfOut o = sphere_eval(radius, load_point(pts, i));
+        out_val[i] = o.val;
+        out_grad[3 * i] = o.grad.x; out_grad[3 * i + 1] = o.grad.y; out_grad[3 * i + 2] = o.grad.z;
+    }
+}
+
+// ============================================================ composed query
+// One thread per (configuration, point): walks the S sub-SDFs in registers --
+// transform into the sub-frame, evaluate, keep the running min (first index on
+// ties, as torch.argmin), rotate the winning gradient back -- and writes
+// (val, grad) once.  The S*|A|*P*3 intermediates of sdf.py:399-415 never exist.
+constexpr int kCompThreads = 256;
+constexpr int kCompMaxSmemSdf = 32;
+
+template <bool kMesh>
+__global__ void __launch_bounds__(kCompThreads)
+composed_query_kernel(const pvb_sdf_desc *__restrict__ descs, int n_sdf, const float *__restrict__ xforms,
+                      int n_cfg, int cfg_begin, int cfg_count,
+                      const float *__restrict__ pts, long long n_pts, uint32_t mesh_mode,
+                      float *__restrict__ out_val, float *__restrict__ out_grad, int *__restrict__ out_which) {
+    __shared__ pvb_sdf_desc s_desc[kCompMaxSmemSdf];
+    __shared__ float s_xf[kCompMaxSmemSdf][12];
+    const bool use_smem = n_sdf <= kCompMaxSmemSdf;
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    if (use_smem) {
+        // descriptors are configuration independent: stage them once per block
+        const int words = n_sdf * (int)(sizeof(pvb_sdf_desc) / 4);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(descs);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_desc);
+        for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+    }
+    for (int c = blockIdx.y; c < cfg_count; c += gridDim.y) {
+        const int cfg = cfg_begin + c;
+        __syncthreads();
+        if (use_smem) {
+            for (int w = threadIdx.x; w < n_sdf * 12; w += blockDim.x) {
+                const int s = w / 12, e = w % 12;
+                s_xf[s][e] = xforms[((size_t)s * n_cfg + cfg) * 16 + e];
+            }
+        }
+        __syncthreads();
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
+            const f3 p = load_point(pts, i);
+            float best = PVB_INF;
+            f3 bg = mk3(0.f, 0.f, 0.f);
+            int bs = -1;
+            for (int s = 0; s < n_sdf; ++s) {
+                const pvb_sdf_desc &d = use_smem ? s_desc[s] : descs[s];
+                const float *xf = use_smem ? s_xf[s] : xforms + ((size_t)s * n_cfg + cfg) * 16;
+                // Transform3d.transform_points: R p + t  (sdf.py:399)
+                const f3 q = mk3(fmaf(xf[0], p.x, fmaf(xf[1], p.y, fmaf(xf[2], p.z, xf[3]))),
+                                 fmaf(xf[4], p.x, fmaf(xf[5], p.y, fmaf(xf[6], p.z, xf[7]))),
+                                 fmaf(xf[8], p.x, fmaf(xf[9], p.y, fmaf(xf[10], p.z, xf[11]))));
+                // exact pruning: a sub-SDF whose value is provably > best cannot be the argmin
+                if (bs >= 0) {
+                    if (d.kind == PVB_KIND_GRID && (d.flags & PVB_GRID_PRUNE_OK)) {
+                        if (aabb_lower_bound(d, q) - d.prune_margin > best) continue;
+                    }
+                }
+                SdfOut o;
+                const uint64_t idx = ((uint64_t)c * (uint64_t)n_pts + (uint64_t)i) * (uint64_t)n_sdf + (uint64_t)s;
+                if (d.kind == PVB_KIND_GRID) o = grid_eval<kMesh>(d, st, q, mesh_mode, idx, nullptr);
+                else if (kMesh && d.kind == PVB_KIND_MESH) o = mesh_eval(d, st, q, mesh_mode, idx, nullptr, nullptr);
+                else o = sphere_eval(d.radius, q);
+                if (o.val < best || bs < 0) {   // strict <: first index wins ties (torch.argmin, sdf.py:421)
+                    best = o.val; bg = o.grad; bs = s;
+                }
+            }
+            // link_frame_to_obj_frame[i].transform_normals(g) = g @ inv(inv(M)[:3,:3]) = g @ M[:3,:3]
+            // (sdf.py:380-383, 409): the double inversion cancels, no inverse is needed.
+            const float *G = use_smem ? s_xf[max(bs, 0)] : xforms + ((size_t)max(bs, 0) * n_cfg + cfg) * 16;
+            const f3 go = mk3(fmaf(bg.x, G[0], fmaf(bg.y, G[4], bg.z * G[8])),
+                              fmaf(bg.x, G[1], fmaf(bg.y, G[5], bg.z * G[9])),
+                              fmaf(bg.x, G[2], fmaf(bg.y, G[6], bg.z * G[10])));
+            const long long o_i = (long long)c * n_pts + i;
+            out_val[o_i] = best;
+            out_grad[3 * o_i] = go.x; out_grad[3 * o_i + 1] = go.y; out_grad[3 * o_i + 2] = go.z;
+            if (out_which) out_which[o_i] = bs;
+        }
+    }
+}
+
+// =================================================================== chamfer
+// grid = (tiles, n_tf).  Each block: transform its points with W_b, unsigned
+// distance (no sign pass: the value is squared, chamfer.py:92), block-reduce
+// (scale*d)^2 into one partial; a second tiny kernel sums the partials in a
+// fixed order (deterministic) and divides by N.
+constexpr int kChamThreads = 256;
+
+__global__ void __launch_bounds__(kChamThreads)
+chamfer_partial_kernel(const pvb_sdf_desc obj, const float *__restrict__ w2o, const float *__restrict__ pts,
+                       long long n_pts, float scale, int n_stage_max, float *__restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ float s_red[kChamThreads / 32];
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    if (obj.kind == PVB_KIND_MESH) st = stage_nodes(obj.nodes, obj.n_nodes, n_stage_max, smem_raw, &bar);
+    const float *W = w2o + (size_t)blockIdx.y * 16;
+    float xf[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) xf[e] = __ldg(W + e);
+    float acc = 0.f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
+        const f3 p = load_point(pts, i);
+        const f3 q = mk3(fmaf(xf[0], p.x, fmaf(xf[1], p.y, fmaf(xf[2], p.z, xf[3]))),
+                         fmaf(xf[4], p.x, fmaf(xf[5], p.y, fmaf(xf[6], p.z, xf[7]))),
+                         fmaf(xf[8], p.x, fmaf(xf[9], p.y, fmaf(xf[10], p.z, xf[11]))));
+        float d;
+        if (obj.kind == PVB_KIND_MESH) {
+            const Closest c = bvh_closest(reinterpret_cast<const float4 *>(obj.nodes), st,
+                                          reinterpret_cast<const float4 *>(obj.tris), q, PVB_INF);
+            const f3 g = c.q - q;
+            d = sqrtf(fmaf(g.x, g.x, fmaf(g.y, g.y, g.z * g.z)));
+        } else if (obj.kind == PVB_KIND_GRID) {
+            d = grid_eval<true>(obj, st, q, PVB_MESH_DEFAULT, (uint64_t)i, nullptr).val;
+        } else {
+            d = sphere_eval(obj.radius, q).val;
+        }
+        const float sd = scale * d;
+        acc = fmaf(sd, sd, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < kChamThreads / 32; ++w) s += s_red[w];
+        partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+__global__ void chamfer_finish_kernel(const float *__restrict__ partial, int n_blk, long long n_pts,
+                                      float *__restrict__ out) {
+    // one warp per transform, fixed summation order
+    const int b = blockIdx.x;
+    double s = 0.0;
+    for (int k = threadIdx.x; k < n_blk; k += 32) s += (double)partial[(size_t)b * n_blk + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[b] = (float)(s / (double)n_pts);
+}
+
+// ==================================================================== sample
+// Philox4x32-10 counter RNG (Salmon et al. 2011): sample i uses counter (i, 0, 0, 0).
+__device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0,
+                                             uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+__global__ void mesh_sample_kernel(const double *__restrict__ verts, const int *__restrict__ faces, long long n_faces,
+                                   const long long *__restrict__ cum, long long n, unsigned long long seed,
+                                   double *__restrict__ out_pts, int *__restrict__ out_face) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // first face whose inclusive cumulative count exceeds i
+        long long lo = 0, hi = n_faces - 1;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (cum[mid] > i) hi = mid; else lo = mid + 1;
+        }
+        const int f = (int)lo;
+        uint32_t c0 = (uint32_t)i, c1 = (uint32_t)((unsigned long long)i >> 32), c2 = 0u, c3 = 0u;
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            philox_round(c0, c1, c2, c3, k0, k1);
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        const double r1 = ((double)(((unsigned long long)c0 << 21) ^ (unsigned long long)(c1 >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        const double r2 = ((double)(((unsigned long long)c2 << 21) ^ (unsigned long long)(c3 >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        const double sr = sqrt(r1);
+        const double a = 1.0 - sr, b = sr * (1.0 - r2), c = sr * r2;   // sdf.py:654 (Open3D area-uniform rule)
+        const int i0 = faces[3 * (size_t)f], i1 = faces[3 * (size_t)f + 1], i2 = faces[3 * (size_t)f + 2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            out_pts[3 * i + k] = a * verts[3 * (size_t)i0 + k] + b * verts[3 * (size_t)i1 + k] + c * verts[3 * (size_t)i2 + k];
+        if (out_face) out_face[i] = f;
+    }
+}
+
+// ======================================================== transform points
+__global__ void transform_points_kernel(const float *__restrict__ xforms, int n_tf, const float *__restrict__ pts,
+                                        long long n_pts, float *__restrict__ out) {
+    const int b = blockIdx.y;
+    const float *xf = xforms + (size_t)b * 16;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
+        const f3 p = load_point(pts, i);
+        float *o = out + ((size_t)b * n_pts + i) * 3;
+        o[0] = fmaf(xf[0], p.x, fmaf(xf[1], p.y, fmaf(xf[2], p.z, xf[3])));
+        o[1] = fmaf(xf[4], p.x, fmaf(xf[5], p.y, fmaf(xf[6], p.z, xf[7])));
+        o[2] = fmaf(xf[8], p.x, fmaf(xf[9], p.y, fmaf(xf[10], p.z, xf[11])));
+    }
+}
+
+static int grid_for(long long work_items, int threads, int blocks_per_sm) {
+    const long long want = (work_items + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * blocks_per_sm;
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+// shared-memory budget for the staged top of the tree
+static int stage_nodes_for(int n_nodes) {
+    const int max_nodes = 384;   // 48 KB
+    return n_nodes < max_nodes ? n_nodes : max_nodes;
+}
+
+}  // namespace pvb
+
+using namespace pvb;
+
+// ======================================================================= ABI
+static int check_mesh(const pvb_sdf_desc *m, const char *who) {
+    if (!m->nodes || !m->tris || m->n_nodes < 1 || m->n_tris < 1) {
+        pvb_set_error("%s: mesh part of the descriptor is empty", who);
+        return PVB_ERR_INVALID;
+    }
+    return PVB_OK;
+}
+
+extern "C" int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_t n, uint32_t mode, float *out_dist,
+                              float *out_grad, float *out_closest, int32_t *out_face, float *out_normal, void *stream) {
+    if (!mesh || n < 0 || (n > 0 && (!pts || !out_dist || !out_grad))) {
+        pvb_set_error("pvb_mesh_query: null argument");
+        return PVB_ERR_INVALID;
+    }
+    if (int rc = check_mesh(mesh, "pvb_mesh_query")) return rc;
+    if ((mode & PVB_MESH_SURFACE_NORMAL) && !mesh->face_normals) {
+        pvb_set_error("pvb_mesh_query: face_normals required for PVB_MESH_SURFACE_NORMAL");
+        return PVB_ERR_INVALID;
+    }
+    if (out_normal && !mesh->face_normals) {
+        pvb_set_error("pvb_mesh_query: face_normals required for out_normal");
+        return PVB_ERR_INVALID;
+    }
+    if (n == 0) return PVB_OK;
+    const int n_stage = stage_nodes_for(mesh->n_nodes);
+    const size_t smem = (size_t)n_stage * 128;
+    const int blocks = grid_for(n, kMeshThreads, 8);
+    mesh_query_kernel<<<blocks, kMeshThreads, smem, (cudaStream_t)stream>>>(*mesh, pts, n, mode, n_stage, out_dist,
+                                                                            out_grad, out_closest, out_face, out_normal);
+    PVB_CHECK_LAUNCH("pvb_mesh_query");
+    return PVB_OK;
+}
+
+extern "C" int pvb_grid_lookup(const pvb_sdf_desc *grid, const float *pts, int64_t n, float *out_val, float *out_grad,
+                               uint8_t *out_outside, float surface_level, int64_t *out_index, void *stream) {
+    if (!grid || n < 0 || (n > 0 && !pts)) {
+        pvb_set_error("pvb_grid_lookup: null argument");
+        return PVB_ERR_INVALID;
+    }
+    if (!grid->table || grid->dims[0] < 1 || grid->dims[1] < 1 || grid->dims[2] < 1) {
+        pvb_set_error("pvb_grid_lookup: grid part of the descriptor is empty");
+        return PVB_ERR_INVALID;
+    }
+    if (grid->flags & PVB_GRID_OOB_GT)
+        if (int rc = check_mesh(grid, "pvb_grid_lookup(LOOKUP_GT_SDF)")) return rc;
+    if (n == 0) return PVB_OK;
+    const uint32_t mesh_mode = PVB_MESH_DEFAULT;
+    const bool gt = (grid->flags & PVB_GRID_OOB_GT) != 0;
+    auto aligned = [](const void *p, size_t a) { return p == nullptr || ((uintptr_t)p % a) == 0; };
+    const bool vec_ok = aligned(pts, 16) && aligned(out_val, 16) && aligned(out_grad, 16) && aligned(out_outside, 4) &&
+                        aligned(out_index, 16);
+    const long long n_quads = vec_ok ? n / 4 : 0;
+    if (n_quads > 0) {
+        const int blocks = grid_for(n_quads, kGridThreads, 8);
+        auto kern = gt ? grid_lookup_vec4_kernel<true> : grid_lookup_vec4_kernel<false>;
+        kern<<<blocks, kGridThreads, 0, (cudaStream_t)stream>>>(
+            *grid, reinterpret_cast<const float4 *>(pts), n_quads, mesh_mode, reinterpret_cast<float4 *>(out_val),
+            reinterpret_cast<float4 *>(out_grad), reinterpret_cast<uchar4 *>(out_outside), surface_level,
+            reinterpret_cast<longlong2 *>(out_index));
+        PVB_CHECK_LAUNCH("pvb_grid_lookup(vec4)");
+    }
+    const long long first = 4 * n_quads;
+    if (first < n) {
+        const int blocks = grid_for(n - first, kGridThreads, 8);
+        auto kern = gt ? grid_lookup_scalar_kernel<true> : grid_lookup_scalar_kernel<false>;
+        kern<<<blocks, kGridThreads, 0, (cudaStream_t)stream>>>(
+            *grid, pts, first, n, mesh_mode, out_val, out_grad, out_outside, surface_level, (long long *)out_index);
+        PVB_CHECK_LAUNCH("pvb_grid_lookup(scalar)");
+    }
+    return PVB_OK;
+}
+
+extern "C" int pvb_sphere_query(float radius, const float *pts, int64_t n, float *out_val, float *out_grad,
+                                void *stream) {
+    if (n < 0 || (n > 0 && (!pts || !out_val || !out_grad))) {
+        pvb_set_error("pvb_sphere_query: null argument");
+        return PVB_ERR_INVALID;
+    }
+    if (n == 0) return PVB_OK;
+    sphere_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(radius, pts, n, out_val, out_grad);
+    PVB_CHECK_LAUNCH("pvb_sphere_query");
+    return PVB_OK;
+}
+
+extern "C" int pvb_composed_query(const void *descs_dev, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
+                                  int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count,
+                                  const float *pts, int64_t n_pts, uint32_t mesh_mode, float *out_val, float *out_grad, int32_t *out_which,
+                                  void *stream) {
+    if (!descs_dev || !xforms || n_sdf < 1 || n_cfg < 1 || cfg_begin < 0 || cfg_count < 0 ||
+        cfg_begin + cfg_count > n_cfg || n_pts < 0 || (n_pts > 0 && cfg_count > 0 && (!pts || !out_val || !out_grad))) {
+        pvb_set_error("pvb_composed_query: invalid argument (n_sdf=%d n_cfg=%d cfg=[%d,+%d) n_pts=%lld)", n_sdf, n_cfg,
+                      cfg_begin, cfg_count, (long long)n_pts);
+        return PVB_ERR_INVALID;
+    }
+    if (n_pts == 0 || cfg_count == 0) return PVB_OK;
+    const int gx = grid_for(n_pts, kCompThreads, 8);
+    int gy = cfg_count < 65535 ? cfg_count : 65535;
+    // keep the total block count bounded for huge config batches
+    const long long cap = (long long)sm_count() * 64;
+    if ((long long)gx * gy > cap) { gy = (int)(cap / gx); if (gy < 1) gy = 1; }
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    auto kern = needs_mesh ? composed_query_kernel<true> : composed_query_kernel<false>;
+    kern<<<grid, kCompThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const pvb_sdf_desc *>(descs_dev), n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts,
+        n_pts, mesh_mode, out_val, out_grad, out_which);
+    PVB_CHECK_LAUNCH("pvb_composed_query");
+    return PVB_OK;
+}
+
+extern "C" int64_t pvb_chamfer_workspace(int64_t n_pts) {
+    return (int64_t)grid_for(n_pts < 1 ? 1 : n_pts, kChamThreads, 4);
+}
+
+extern "C" int pvb_chamfer(const pvb_sdf_desc *obj, const float *world_to_object, int32_t n_tf, const float *pts,
+                           int64_t n_pts, float scale, float *workspace, float *out, void *stream) {
+    if (!obj || !world_to_object || n_tf < 0 || n_pts < 1 || !pts || !workspace || !out) {
+        pvb_set_error("pvb_chamfer: invalid argument");
+        return PVB_ERR_INVALID;
+    }
+    if (obj->kind == PVB_KIND_MESH)
+        if (int rc = check_mesh(obj, "pvb_chamfer")) return rc;
+    if (n_tf == 0) return PVB_OK;
+    if (n_tf > 65535) {
+        pvb_set_error("pvb_chamfer: at most 65535 transforms per call (got %d)", n_tf);
+        return PVB_ERR_INVALID;
+    }
+    const int n_blk = (int)pvb_chamfer_workspace(n_pts);
+    const int n_stage = obj->kind == PVB_KIND_MESH ? stage_nodes_for(obj->n_nodes) : 0;
+    dim3 grid((unsigned)n_blk, (unsigned)n_tf);
+    chamfer_partial_kernel<<<grid, kChamThreads, (size_t)n_stage * 128, (cudaStream_t)stream>>>(
+        *obj, world_to_object, pts, n_pts, scale, n_stage, workspace);
+    PVB_CHECK_LAUNCH("pvb_chamfer(partial)");
+    chamfer_finish_kernel<<<n_tf, 32, 0, (cudaStream_t)stream>>>(workspace, n_blk, n_pts, out);
+    PVB_CHECK_LAUNCH("pvb_chamfer(finish)");
+    return PVB_OK;
+}
+
+extern "C" int pvb_mesh_sample(const double *verts64, const int32_t *faces, int64_t n_faces, const int64_t *cum_counts,
+                               int64_t n, uint64_t seed, double *out_pts, int32_t *out_face, void *stream) {
+    if (!verts64 || !faces || !cum_counts || n_faces < 1 || n < 0 || (n > 0 && !out_pts)) {
+        pvb_set_error("pvb_mesh_sample: invalid argument");
+        return PVB_ERR_INVALID;
+    }
+    if (n == 0) return PVB_OK;
+    mesh_sample_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        verts64, faces, n_faces, (const long long *)cum_counts, n, seed, out_pts, out_face);
+    PVB_CHECK_LAUNCH("pvb_mesh_sample");
+    return PVB_OK;
+}
+
+extern "C" int pvb_transform_points(const float *xforms, int32_t n_tf, const float *pts, int64_t n_pts, float *out,
+                                    void *stream) {
+    if (!xforms || n_tf < 0 || n_pts < 0 || (n_tf > 0 && n_pts > 0 && (!pts || !out)) || n_tf > 65535) {
+        pvb_set_error("pvb_transform_points: invalid argument");
+        return PVB_ERR_INVALID;
+    }
+    if (n_tf == 0 || n_pts == 0) return PVB_OK;
+    dim3 grid((unsigned)grid_for(n_pts, 256, 8), (unsigned)n_tf);
+    transform_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xforms, n_tf, pts, n_pts, out);
+    PVB_CHECK_LAUNCH("pvb_transform_points");
+    return PVB_OK;
+}

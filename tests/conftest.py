@@ -1,0 +1,38 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """libpvb.so, compiled if missing (nvcc cross-compiles for sm_100a without a GPU)."""
+    from pytorch_volumetric_b200 import _native
+    if _native.needs_build():
+        _native.build()
+    return _native.lib()
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    from oracle import _geom
+    _geom.build()
+    return _geom.lib()

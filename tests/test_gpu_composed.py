@@ -1,0 +1,234 @@
+"""GPU parity: ComposedSDF (reference sdf.py:332-433) and RobotSDF (model_to_sdf.py:12-125)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import workloads
+from helpers import golden, pv_factory
+from test_gpu_cached import _cached_from_golden
+
+pytestmark = pytest.mark.gpu
+
+WRENCH_URDF = """<robot name="wrench">
+{links}
+  <link name="offset_wrench"><visual><geometry><mesh filename="wrench.obj"/></geometry></visual></link>
+{joints}
+</robot>"""
+
+
+def write_wrench_urdf(dirname):
+    """Procedural equivalent of the reference's tests/offset_wrench.urdf: 3 prismatic + 3 revolute joints
+    (x, y, z each) in front of one mesh link."""
+    from pytorch_volumetric_b200.meshio import write_obj
+    v, f = workloads.fixture_mesh("wrench")
+    write_obj(os.path.join(dirname, "wrench.obj"), v, f)
+    names = ["link_x_trans", "link_y_trans", "link_z_trans", "link_x_rot", "link_y_rot", "link_z_rot", "offset_wrench"]
+    links = "\n".join(f'  <link name="{n}"/>' for n in names[:-1])
+    axes = ["1 0 0", "0 1 0", "0 0 1"] * 2
+    jn = ["x_trans", "y_trans", "z_trans", "x_rot", "y_rot", "z_rot"]
+    joints = "\n".join(
+        f'  <joint name="{jn[i]}" type="{"prismatic" if i < 3 else "revolute"}"><origin rpy="0 0 0" xyz="0 0 0"/>'
+        f'<parent link="{names[i]}"/><child link="{names[i + 1]}"/><axis xyz="{axes[i]}"/></joint>' for i in range(6))
+    path = os.path.join(dirname, "offset_wrench.urdf")
+    with open(path, "w") as fh:
+        fh.write(WRENCH_URDF.format(links=links, joints=joints))
+    return path
+
+
+def _close(a, b, tol=1e-5):
+    return np.abs(a - b) <= tol
+
+
+def _composed_from_golden(tmp_path):
+    import pytorch_volumetric_b200 as pv
+    zc = golden("ref_cachedsdf_probe")
+    cs = _cached_from_golden(zc, "probe", tmp_path)
+    z = golden("ref_composed")
+    S, A = int(z["S"]), int(z["A"])
+    sdfs = [cs, cs, pv.SphereSDF(float(z["sphere_radius"])), cs]
+    return pv, z, S, A, sdfs
+
+
+def test_composed_vs_reference_golden(tmp_path):
+    pv, z, S, A, sdfs = _composed_from_golden(tmp_path)
+    tmat = torch.from_numpy(z["tmat"]).cuda()
+    q = torch.from_numpy(z["q"]).cuda()
+    comp = pv.ComposedSDF(sdfs, pv.Transform3d(matrix=tmat[:S]))
+    v, g = comp(q)
+    assert v.shape == (len(q),) and g.shape == (len(q), 3)           # flat output without a config batch (B2)
+    ok = _close(v.cpu().numpy(), z["val_plain"])
+    # an fp32 rigid transform in front of a nearest-voxel lookup flips a few keys at cell boundaries
+    assert (~ok).mean() < 2e-3
+    gok = _close(g.cpu().numpy(), z["grad_plain"]).all(-1)
+    assert (~gok).mean() < 4e-3
+    comp.set_transforms(pv.Transform3d(matrix=tmat), batch_dim=(A,))
+    vb, gb = comp(q.reshape(30, 100, 3))
+    assert vb.shape == (A, 30, 100) and gb.shape == (A, 30, 100, 3)
+    assert (~_close(vb.cpu().numpy(), z["val_batched"])).mean() < 2e-3
+    assert (~_close(gb.cpu().numpy(), z["grad_batched"]).all(-1)).mean() < 4e-3
+    bb = comp.surface_bounding_box(padding=0.01)
+    np.testing.assert_allclose(bb.cpu().numpy(), z["bbox_batched"], atol=1e-6)
+    # batched == per-configuration loop, exactly (tests/test_model_to_sdf.py:206-212)
+    for a in range(A):
+        comp_a = pv.ComposedSDF(sdfs, pv.Transform3d(matrix=tmat.reshape(S, A, 4, 4)[:, a]))
+        va, ga = comp_a(q)
+        assert torch.equal(va, vb[a].reshape(-1)) and torch.equal(ga, gb[a].reshape(-1, 3))
+
+
+def test_composed_fused_equals_generic_path(tmp_path):
+    """The fused kernel (incl. its AABB pruning) against the unfused per-SDF composition of the same package, and
+    against a user-defined ObjectFrameSDF subclass that forces the generic path."""
+    pv, z, S, A, sdfs = _composed_from_golden(tmp_path)
+
+    class Opaque(pv.ObjectFrameSDF):          # no native descriptor -> generic path
+        def __init__(self, inner):
+            self.inner = inner
+
+        def __call__(self, p):
+            return self.inner(p)
+
+        def surface_bounding_box(self, **kw):
+            return self.inner.surface_bounding_box(**kw)
+
+    tmat = torch.from_numpy(z["tmat"]).cuda()
+    q = torch.from_numpy(z["q"]).cuda()
+    fused = pv.ComposedSDF(sdfs, pv.Transform3d(matrix=tmat))
+    generic = pv.ComposedSDF([Opaque(s) for s in sdfs], pv.Transform3d(matrix=tmat))
+    vf, gf, wf = fused.query(q, return_which=True)
+    vg, gg, wg = generic.query(q, return_which=True)
+    assert torch.equal(wf, wg)
+    assert torch.equal(vf, vg)
+    assert (gf - gg).abs().max() < 1e-6
+    # argmin semantics: first index on ties -- two identical SDFs at the same pose must report index 0
+    twin = pv.ComposedSDF([sdfs[0], sdfs[0]], pv.Transform3d(matrix=tmat[:1].repeat(2, 1, 1)))
+    _, _, w = twin.query(q, return_which=True)
+    assert int(w.max()) == 0
+
+
+def test_composed_of_meshes_vs_oracle():
+    """ComposedSDF([MeshSDF, MeshSDF], translations) as in tests/test_sdf.py:61-80, checked against the oracle."""
+    import pytorch_volumetric_b200 as pv
+    from oracle import port, tp_pytorch_kinematics as opk
+    obj = pv_factory("probe", ray_seed=1)
+    tm = torch.eye(4).repeat(2, 1, 1)
+    tm[0, :3, 3] = torch.tensor([0.1, 0.0, 0.0])
+    tm[1, :3, 3] = torch.tensor([-0.2, 0.0, 0.2])
+    comp = pv.ComposedSDF([pv.MeshSDF(obj), pv.MeshSDF(obj)], pv.Transform3d(matrix=tm.cuda()))
+    q = workloads.uniform_points(4000, (-0.2, -0.05, -0.1), (0.3, 0.05, 0.3), seed=4)
+    v, g = comp(q.cuda())
+    pv_, pf_ = workloads.fixture_mesh("probe")
+    mesh = port.MeshPort(vertices=pv_, faces=pf_)
+    ref = port.ComposedSDFPort([port.MeshSDFPort(mesh), port.MeshSDFPort(mesh)], opk.Transform3d(matrix=tm))
+    np.random.seed(0)
+    vr, gr = ref(q)
+    assert (v.cpu() - vr).abs().max() < 1e-5
+    assert ((g.cpu() - gr).abs().max(dim=-1).values > 1e-5).float().mean() < 2e-3
+
+
+def test_robot_vs_reference_golden(tmp_path):
+    import pytorch_volumetric_b200 as pv
+    z = golden("ref_robot_wrench")
+    urdf = write_wrench_urdf(str(tmp_path))
+    chain = pv.build_serial_chain_from_urdf(open(urdf).read(), "offset_wrench").to(device="cuda")
+    # preload the link table the reference built (same cache format / key)
+    v, f = workloads.fixture_mesh("wrench")
+    bb = np.stack([v.min(0), v.max(0)], axis=1)
+    rng = bb.copy(); rng[:, 0] -= 0.05; rng[:, 1] += 0.05
+    ranges = pv.get_divisible_range_by_resolution(0.004, rng)
+    np.testing.assert_allclose(np.array(ranges), z["ranges"], atol=1e-12)
+    shape = [int(s) for s in z["table_shape"]]
+    cache_path = str(tmp_path / "robot_cache.pkl")
+    torch.save({f"wrench.obj 0.004 {tuple(ranges)}": (torch.from_numpy(z["table_val"]).reshape(shape),
+                                                       torch.from_numpy(z["table_grad"]))}, cache_path)
+    rs = pv.RobotSDF(chain, path_prefix=str(tmp_path),
+                     link_sdf_cls=pv.cache_link_sdf_factory(resolution=0.004, padding=0.05, device="cuda",
+                                                            cache_path=cache_path))
+    th = torch.from_numpy(z["th"]).cuda()
+    rs.set_joint_configuration(th)
+    # FK + offset composition: object->link transforms (model_to_sdf.py:99-113)
+    np.testing.assert_allclose(rs.object_to_link_frames.get_matrix().cpu().numpy(), z["obj_to_link"], atol=2e-6)
+    q = torch.from_numpy(z["q"]).cuda()
+    val, grad = rs(q)
+    assert val.shape == (5, len(q)) and grad.shape == (5, len(q), 3)
+    ok = _close(val.cpu().numpy(), z["val"])
+    assert (~ok).mean() < 3e-3          # voxel-boundary flips after the fp32 transform
+    gok = _close(grad.cpu().numpy(), z["grad"]).all(-1)
+    assert (~gok).mean() < 5e-3
+    np.testing.assert_allclose(rs.surface_bounding_box(padding=0.05).cpu().numpy(), z["bbox"], atol=1e-5)
+
+
+def test_single_link_robot_contract(tmp_path):
+    """The shape / value contracts of the reference's tests/test_model_to_sdf.py:263-326."""
+    import pytorch_volumetric_b200 as pv
+    urdf = write_wrench_urdf(str(tmp_path))
+    chain = pv.build_serial_chain_from_urdf(open(urdf).read(), "offset_wrench").to(device="cuda")
+    sdf = pv.RobotSDF(chain, path_prefix=str(tmp_path),
+                      link_sdf_cls=pv.cache_link_sdf_factory(resolution=0.001, padding=0.05, device="cuda",
+                                                             cache_path=str(tmp_path / "c.pkl")))
+    th = torch.zeros(6, device="cuda")
+    sdf.set_joint_configuration(th.view(1, -1))
+    query_range = sdf.surface_bounding_box(padding=0.05)[0]
+    coords, pts = pv.get_coordinates_and_points_in_grid(0.001, query_range.cpu(), device="cuda")
+    sdf_val, sdf_grad = sdf(pts)
+    assert sdf_val.shape == (1, len(pts)) and sdf_grad.shape == (1, len(pts), 3)
+    near_surface = sdf_val[0].abs() < 0.001
+    surf_pts = pts[near_surface]
+    B = 5
+    sdf.set_joint_configuration(th.view(1, -1).repeat(B, 1))
+    query_range = sdf.surface_bounding_box(padding=0.05)
+    assert query_range.shape == (B, 3, 2)
+    for i in range(1, B):
+        assert torch.allclose(query_range[0], query_range[i])
+    BB, N = 10, 100
+    assert surf_pts.shape[0] > BB * N
+    test_pts = surf_pts[:BB * N]
+    sdf_vals, sdf_grads = sdf(test_pts)
+    assert sdf_vals.shape == (B, BB * N) and sdf_grads.shape == (B, BB * N, 3)
+    assert torch.allclose(sdf_vals.abs(), torch.zeros_like(sdf_vals), atol=1e-3)
+    batch_sdf_vals, batch_sdf_grads = sdf(test_pts.view(BB, N, 3))
+    assert batch_sdf_vals.shape == (B, BB, N) and batch_sdf_grads.shape == (B, BB, N, 3)
+    assert torch.allclose(batch_sdf_vals, sdf_vals.view(B, BB, N))
+    lb = sdf.link_bounding_boxes()
+    assert lb.shape == (B, 8, 3)
+
+
+def test_robot_arm_batched_equals_looped(tmp_path):
+    """tests/test_model_to_sdf.py:173-212 on the synthetic 7-DOF arm: one batched call == per-configuration loop,
+    and the fused kernel == an independent torch recomposition of the per-link lookups."""
+    import pytorch_volumetric_b200 as pv
+    urdf, end = workloads.write_arm(str(tmp_path))
+    chain = pv.build_serial_chain_from_urdf(open(urdf).read(), end).to(device="cuda")
+    s = pv.RobotSDF(chain, path_prefix=str(tmp_path),
+                    link_sdf_cls=pv.cache_link_sdf_factory(resolution=0.02, padding=1.0, device="cuda",
+                                                           cache_path=str(tmp_path / "arm.pkl")))
+    assert len(s.sdf.sdfs) == 8
+    th = workloads.arm_configurations(20).cuda()
+    s.set_joint_configuration(th)
+    coords, pts = pv.get_coordinates_and_points_in_grid(0.01, np.array([[-1, 0.5], [0.02, 0.02], [-0.2, 0.8]]),
+                                                        device="cuda")
+    assert len(pts) == 15251
+    all_val, all_grad = s(pts)
+    assert all_val.shape == (20, 15251)
+    for i in range(0, 20, 3):
+        s.set_joint_configuration(th[i])
+        v, g = s(pts)
+        assert v.shape == (15251,)
+        assert torch.equal(v, all_val[i]) and torch.equal(g, all_grad[i])
+    # independent recomposition: per-link CachedSDF calls on explicitly transformed points, argmin in torch
+    s.set_joint_configuration(th)
+    M = s.object_to_link_frames.get_matrix().reshape(8, 20, 4, 4)
+    vals, grads = [], []
+    for i, link in enumerate(s.sdf.sdfs):
+        local = pts @ M[i, :, :3, :3].transpose(-1, -2) + M[i, :, :3, 3].unsqueeze(1)
+        v, g = link(local)
+        vals.append(v); grads.append(g @ M[i, :, :3, :3])
+    vals = torch.stack(vals); grads = torch.stack(grads)
+    which = vals.argmin(0)
+    v_ref = vals.gather(0, which.unsqueeze(0))[0]
+    g_ref = grads.gather(0, which[None, ..., None].expand(1, -1, -1, 3))[0]
+    frac = ((all_val - v_ref).abs() > 1e-6).float().mean()
+    assert frac < 1e-3, frac        # bmm-vs-fma rounding of the transform flips a few voxel keys
+    assert ((all_grad - g_ref).abs().max(-1).values > 1e-5).float().mean() < 2e-3

@@ -1,0 +1,123 @@
+"""GPU parity: MeshSDF / ObjectFactory closest-point query (reference sdf.py:122-172) against the CPU oracle
+(brute force) and against the golden vectors produced by the reference source over the third-party shims."""
+import numpy as np
+import pytest
+import torch
+
+import workloads
+from helpers import golden, port_mesh, pv_factory, ray_noise, classify_mesh_mismatch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # north_star: "all within 1e-5 of the reference"
+
+
+def _query_points(name, n, seed, pad=0.02):
+    v, _ = workloads.fixture_mesh(name)
+    lo, hi = v.min(0) - pad, v.max(0) + pad
+    return workloads.uniform_points(n, lo, hi, seed)
+
+
+@pytest.mark.parametrize("name,n", [("probe", 20000), ("wrench", 20000), ("drill", 6000),
+                                    ("scene_overlap", 5000), ("scene_separated", 5000)])
+def test_mesh_query_vs_oracle(name, n):
+    obj = pv_factory(name, ray_seed=5)
+    mesh = port_mesh(name)
+    pts = _query_points(name, n, seed=21)
+    res = obj.object_frame_closest_point(pts.cuda(), compute_normal=True)
+    # the oracle gets the same per-point ray directions through the host mirror of the kernel's jitter hash
+    c_ref, d_ref, g_ref, n_ref = mesh.closest_point(pts, compute_normal=True, ray_noise=ray_noise(5, n))
+    d_gpu, g_gpu = res.distance.cpu().numpy(), res.gradient.cpu().numpy()
+    d_ref, g_ref = d_ref.numpy(), g_ref.numpy()
+    # unsigned distance: fp32 Ericson on both sides, differs only by FMA contraction
+    assert np.abs(np.abs(d_gpu) - np.abs(d_ref)).max() < 1e-6
+    # sign: ray parity must agree except at numerically degenerate grazes
+    sign_bad = (np.sign(d_gpu) != np.sign(d_ref)) & (np.abs(d_ref) > 1e-6)
+    closed = obj.is_closed
+    assert sign_bad.mean() <= (0.0 if closed else 2e-3), f"sign mismatches: {sign_bad.sum()} of {n}"
+    ok = ~sign_bad
+    bad_v, bad_g, rep = classify_mesh_mismatch(d_gpu[ok], g_gpu[ok], d_ref[ok], g_ref[ok], TOL)
+    assert bad_v == 0 and bad_g == 0, rep
+    assert rep["bad_grad"] <= 2e-3 * n, rep
+    # closest point itself
+    assert np.abs(res.closest.cpu().numpy() - c_ref.numpy()).max() < 1e-5 or rep["explained"] > 0
+    # shapes / dtypes / device (sdf.py:166)
+    assert res.distance.shape == (n,) and res.gradient.shape == (n, 3) and res.normal.shape == (n, 3)
+    assert res.distance.dtype == torch.float32 and res.distance.device.type == "cuda"
+
+
+@pytest.mark.parametrize("name", ["probe", "wrench", "drill"])
+def test_mesh_query_vs_reference_golden(name):
+    """Golden vectors = the reference's own sdf.py running over the restated third-party layer."""
+    z = golden(f"ref_meshsdf_{name}")
+    obj = pv_factory(name)
+    pts = torch.from_numpy(z["pts"]).cuda()
+    res = obj.object_frame_closest_point(pts, compute_normal=True)
+    d_gpu, g_gpu = res.distance.cpu().numpy(), res.gradient.cpu().numpy()
+    sign_bad = (np.sign(d_gpu) != np.sign(z["distance"])) & (np.abs(z["distance"]) > 1e-6)
+    assert sign_bad.mean() <= (0.0 if obj.is_closed else 2e-3)
+    ok = ~sign_bad
+    bad_v, bad_g, rep = classify_mesh_mismatch(d_gpu[ok], g_gpu[ok], z["distance"][ok], z["gradient"][ok], TOL)
+    assert bad_v == 0 and bad_g == 0, rep
+    np.testing.assert_allclose(obj.bounding_box(), z["bbox"], rtol=0, atol=0)
+    np.testing.assert_allclose(obj.bounding_box(padding=0.1, padding_ratio=0.05), z["bbox_pad"], rtol=0, atol=1e-15)
+    # the reference's own invariant: sampled surface points have |sdf| < 1e-4 (tests/test_sdf.py:23)
+    import pytorch_volumetric_b200 as pv
+    sdf = pv.MeshSDF(obj)
+    v, g = sdf(torch.from_numpy(z["surf_pts"]).cuda())
+    assert v.abs().max() < 1e-4
+    # on the surface the gradient is the face normal of the closest face; compare where unambiguous
+    cos = (g.cpu().numpy() * z["surf_grad"]).sum(-1)
+    assert (cos > 0.999).mean() > 0.97
+
+
+def test_batched_shapes_and_host_inputs():
+    """tests/test_sdf.py:26-29: (10,100,3) -> (10,100); CPU tensors and ndarrays are accepted and returned on CPU."""
+    import pytorch_volumetric_b200 as pv
+    obj = pv_factory("probe")
+    sdf = pv.MeshSDF(obj)
+    pts = _query_points("probe", 1000, seed=3)
+    v_flat, g_flat = sdf(pts.cuda())
+    v_b, g_b = sdf(pts.view(10, 100, 3).cuda())
+    assert v_b.shape == (10, 100) and g_b.shape == (10, 100, 3)
+    assert torch.equal(v_b.reshape(-1), v_flat) and torch.equal(g_b.reshape(-1, 3), g_flat)
+    v_cpu, g_cpu = sdf(pts)                      # host buffer in, host buffer out
+    assert v_cpu.device.type == "cpu" and torch.equal(v_cpu, v_flat.cpu())
+    q = obj.object_frame_closest_point(pts.double().numpy())      # ndarray -> float32 cpu tensors (sdf.py:129-131)
+    assert q.distance.dtype == torch.float32 and q.distance.device.type == "cpu"
+    v64, _ = sdf(pts.double().cuda())
+    assert v64.dtype == torch.float64
+    # empty input
+    v0, g0 = sdf(torch.zeros(0, 3, device="cuda"))
+    assert v0.shape == (0,) and g0.shape == (0, 3)
+
+
+def test_mesh_query_large_properties():
+    """North-star size (10^7 queries on the 10k-triangle mesh) through size-independent properties:
+    closest point lies on the surface (its own distance is ~0), |grad| = 1, sign matches the radial test of a
+    star-shaped body, and a permutation of the inputs permutes the outputs."""
+    import pytorch_volumetric_b200 as pv
+    v, f = workloads.bumpy_sphere(100, 51)
+    obj = pv.MeshObjectFactory("bumpy10k", mesh=(v, f))
+    assert obj.is_closed and len(f) == 10000
+    n = 10_000_000
+    pts = workloads.uniform_points(n, v.min(0) - 0.05, v.max(0) + 0.05, seed=2, device="cuda")
+    res = obj.object_frame_closest_point(pts)
+    gn = res.gradient.norm(dim=-1)
+    assert (gn - 1).abs().max() < 1e-5
+    far = res.distance.abs() > 2e-3
+    # closest = p - d * grad away from the shell
+    recon = pts - res.distance.unsqueeze(-1) * res.gradient
+    assert (recon - res.closest)[far].abs().max() < 1e-6
+    sub = torch.randperm(n, device="cuda")[:200000]
+    again = obj.object_frame_closest_point(res.closest[sub])
+    assert again.distance.abs().max() < 1e-6
+    perm = torch.randperm(n, device="cuda")[:1_000_000]
+    res_p = obj.object_frame_closest_point(pts[perm])
+    assert torch.equal(res_p.distance.abs(), res.distance[perm].abs())
+    # inside/outside against the analytic radial function of the generating surface (star-shaped about 0)
+    r = pts.norm(dim=-1)
+    th = torch.atan2(pts[:, 1], pts[:, 0])
+    phi = torch.acos((pts[:, 2] / r).clamp(-1, 1))
+    rs = 0.1 * (1 + 0.25 * torch.sin(5 * th) * torch.sin(4 * phi))
+    clear = (r - rs).abs() > 0.004          # away from the faceting error of the triangulation
+    assert torch.equal((res.distance < 0)[clear], (r < rs)[clear])
