@@ -1,0 +1,547 @@
+#!/usr/bin/env python
+"""bench.py -- SDF+grad queries/s of the batched signed-distance query path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|mesh10k|c3|c4|c5] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input.  The default workload is BASELINE.json
+configs[1] (C2): CachedSDF(res=0.005) of the YCB drill, 10^7 random query points (42 % out of range), value +
+gradient.  With N > 1 (torchrun, one rank per GPU) every rank runs the same per-GPU batch on its own seeded points
+(weak scaling; the path partitions over independent points / configurations, so there is no data-path collective);
+`value` is the whole-job aggregate over the max-over-ranks device time.
+
+`--impl reference` times the CPU restatement of the reference (oracle/port.py, torch-cpu, all host threads) on a
+bounded sample of the same workload; the reference itself is pure Python over third-party wheels that are not
+installable in this image, so the oracle port is the reference arm.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import workloads  # noqa: E402
+
+METRIC = "sdf_grad_queries_per_s"
+UNIT = "queries/s"
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh).get(workload)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 6:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, c[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return x
+
+
+# ---------------------------------------------------------------------------------------------- workloads
+class Workload:
+    """name, units per step (per GPU), algorithmic bytes per step, step(i) on resident inputs,
+    step_host(i) through the public API with host buffers."""
+    kernel = ""
+
+
+class C2(Workload):
+    """BASELINE C2: CachedSDF(res=0.005) on the drill, 10^7 uniform points over the cache range inflated 10 % per
+    side (~42 % out of range -> AABB rule), 3 rotating input buffers (120 MB each, > L2)."""
+    name = "c2"
+    kernel = "grid_lookup_vec4_kernel<false>"
+    n_points = 10_000_000
+
+    def __init__(self, rank, n_buffers=3, cache_dir=None):
+        import pytorch_volumetric_b200 as pv
+        v, f = workloads.fixture_mesh("drill")
+        self.obj = pv.MeshObjectFactory("drill", mesh=(v, f))
+        gt = pv.MeshSDF(self.obj)
+        cache = os.path.join(cache_dir or tempfile.gettempdir(), f"pvb_bench_c2_{rank}.pkl")
+        self.sdf = pv.CachedSDF("drill", 0.005, self.obj.bounding_box(padding=0.1), gt, device="cuda",
+                                cache_path=cache, clean_cache=True)
+        lo = np.array([r[0] for r in self.sdf.ranges]); hi = np.array([r[1] for r in self.sdf.ranges])
+        self.lo, self.hi = lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo)
+        self.host = [workloads.uniform_points(self.n_points, self.lo, self.hi, seed=1000 * rank + b).pin_memory()
+                     for b in range(n_buffers)]
+        self.dev = [h.cuda() for h in self.host]
+        self.units = self.n_points
+        n_vox = int(np.prod(self.sdf.voxels.shape))
+        # 12 B point in + 4 B value + 12 B gradient out per query, + the 16 B/voxel table once per launch
+        self.alg_bytes = 28 * self.n_points + 16 * n_vox
+        self.h2d_bytes = 12 * self.n_points
+        self.d2h_bytes = 16 * self.n_points
+        self.launches_per_step = 1
+        self.desc = {"workload": "C2 CachedSDF(drill, res=0.005, 74x66x78 voxels) x 1e7 uniform points "
+                                 "(range +10%/side, ~42% out-of-range -> AABB rule), value+gradient",
+                     "points_per_step_per_gpu": self.n_points, "l2_policy": "inputs > L2 (120 MB in + 160 MB out "
+                     "per step), 3 rotating input buffers", "oob_strategy": "BOUNDING_BOX"}
+
+    def step(self, i):
+        return self.sdf(self.dev[i % len(self.dev)])
+
+    def step_host(self, i):
+        return self.sdf(self.host[i % len(self.host)])
+
+    # CPU arm: the oracle port on the same tables
+    def cpu_setup(self):
+        from oracle import port
+        v, f = workloads.fixture_mesh("drill")
+        mesh = port.MeshPort(vertices=v, faces=f, name="drill")
+        shape = tuple(self.sdf.voxels.shape)
+        self.cpu_sdf = port.CachedSDFPort("drill", 0.005, mesh.bounding_box(padding=0.1), port.MeshSDFPort(mesh),
+                                          tables=(self.sdf.voxels.raw_data.cpu().reshape(shape),
+                                                  self.sdf.voxels_grad.cpu()))
+        self.cpu_sample = 2_000_000
+        self.cpu_pts = self.host[0][:self.cpu_sample].clone()
+        return f"{self.cpu_sample} of the {self.n_points} points of one step (oracle/port.py CachedSDFPort, torch-cpu)"
+
+    def cpu_step(self):
+        self.cpu_sdf(self.cpu_pts)
+        return self.cpu_sample
+
+
+class Mesh10k(Workload):
+    """North-star target: MeshSDF (BVH closest point + ray parity) on the 10 000-triangle bumpy sphere, 10^7
+    uniform points in AABB + 0.05."""
+    name = "mesh10k"
+    kernel = "mesh_query_kernel"
+    n_points = 10_000_000
+
+    def __init__(self, rank, n_buffers=3, cache_dir=None, n_lon=100, n_lat=51):
+        import pytorch_volumetric_b200 as pv
+        v, f = workloads.bumpy_sphere(n_lon, n_lat)
+        self.v, self.f = v, f
+        self.obj = pv.MeshObjectFactory(f"bumpy{len(f)}", mesh=(v, f))
+        self.sdf = pv.MeshSDF(self.obj)
+        self.host = [workloads.uniform_points(self.n_points, v.min(0) - 0.05, v.max(0) + 0.05,
+                                              seed=2 + 1000 * rank + b).pin_memory() for b in range(n_buffers)]
+        self.dev = [h.cuda() for h in self.host]
+        self.units = self.n_points
+        self.alg_bytes = 28 * self.n_points + 48 * len(f) + 128 * self.obj._bvh_host[0].shape[0]
+        self.h2d_bytes = 12 * self.n_points
+        self.d2h_bytes = 16 * self.n_points
+        self.launches_per_step = 1
+        self.desc = {"workload": f"MeshSDF on a closed {len(f)}-triangle bumpy sphere x 1e7 uniform points in "
+                                 f"AABB+0.05 (BVH4 closest point + ray-parity sign + gradient)",
+                     "points_per_step_per_gpu": self.n_points, "l2_policy": "inputs > L2, 3 rotating input buffers",
+                     "note": "tree walk: latency/L1-bound, not HBM-bound; roofline.frac on compulsory bytes"}
+
+    def step(self, i):
+        return self.sdf(self.dev[i % len(self.dev)])
+
+    def step_host(self, i):
+        return self.sdf(self.host[i % len(self.host)])
+
+    def cpu_setup(self):
+        from oracle import port, tp_open3d
+        tp_open3d.QUERY_METHOD = "bvh"        # OpenMP BVH evaluator of the oracle (not the brute-force checker)
+        self.cpu_mesh = port.MeshPort(vertices=self.v, faces=self.f)
+        self.cpu_sample = 400_000
+        self.cpu_pts = self.host[0][:self.cpu_sample].clone()
+        return f"{self.cpu_sample} of the {self.n_points} points of one step (oracle MeshPort over the OpenMP BVH)"
+
+    def cpu_step(self):
+        self.cpu_mesh.closest_point(self.cpu_pts)
+        return self.cpu_sample
+
+
+class C4(Workload):
+    """BASELINE C4: RobotSDF, synthetic iiwa-like 7-DOF arm (8 link meshes), per-link CachedSDF(res 0.02, padding
+    1.0), 200 joint configurations x 100 000 points; with N GPUs the configuration batch is sharded (strong
+    scaling is reported by the driver from the per-N lines; per-GPU work = 200/N configurations)."""
+    name = "c4"
+    kernel = "composed_query_kernel<false>"
+
+    def __init__(self, rank, world=1, n_cfg=200, n_pts=100_000, cache_dir=None):
+        import pytorch_volumetric_b200 as pv
+        from pytorch_volumetric_b200 import distributed as pd
+        d = os.path.join(cache_dir or tempfile.gettempdir(), f"pvb_bench_arm_{rank}")
+        urdf, end = workloads.write_arm(d)
+        chain = pv.build_serial_chain_from_urdf(open(urdf).read(), end).to(device="cuda")
+        self.robot = pv.RobotSDF(chain, path_prefix=d,
+                                 link_sdf_cls=pv.cache_link_sdf_factory(resolution=0.02, padding=1.0, device="cuda",
+                                                                        cache_path=os.path.join(d, "cache.pkl")))
+        self.th = workloads.arm_configurations(n_cfg).cuda()
+        self.robot.set_joint_configuration(self.th)
+        lo = [r[0] for r in workloads.ARM_QUERY_RANGE]; hi = [r[1] for r in workloads.ARM_QUERY_RANGE]
+        self.host = [workloads.uniform_points(n_pts, lo, hi, seed=4 + b).pin_memory() for b in range(3)]
+        self.dev = [h.cuda() for h in self.host]
+        self.begin, self.end = pd.shard_range(n_cfg, rank, world)
+        self.n_pts, self.n_cfg = n_pts, n_cfg
+        self.units = (self.end - self.begin) * n_pts
+        n_vox = sum(int(np.prod(s.voxels.shape)) for s in self.robot.sdf.sdfs)
+        self.n_vox = n_vox
+        self.alg_bytes = 16 * self.units + 12 * n_pts + 64 * 8 * (self.end - self.begin) + 16 * n_vox
+        self.h2d_bytes = 12 * n_pts
+        self.d2h_bytes = 16 * self.units
+        self.launches_per_step = 1
+        self.desc = {"workload": f"C4 RobotSDF synthetic 7-DOF arm (8 links, CachedSDF res=0.02 pad=1.0, "
+                                 f"{n_vox} voxels = {16 * n_vox / 1e6:.0f} MB tables) x {n_cfg} configurations x "
+                                 f"{n_pts} points, configurations sharded over ranks",
+                     "configs_this_rank": self.end - self.begin, "l2_policy": "output 320 MB/step > L2"}
+
+    def step(self, i):
+        return self.robot.sdf.query(self.dev[i % 3], cfg_begin=self.begin, cfg_count=self.end - self.begin)
+
+    def step_host(self, i):
+        v, g = self.robot.sdf.query(self.host[i % 3], cfg_begin=self.begin, cfg_count=self.end - self.begin)
+        return v.cpu(), g.cpu()
+
+
+class C5(Workload):
+    """BASELINE C5: chamfer of a 5*10^6-point cloud against a 50 000-triangle mesh, B=1 transform; the cloud is
+    sharded over ranks."""
+    name = "c5"
+    kernel = "chamfer_partial_kernel"
+
+    def __init__(self, rank, world=1, n_pts=5_000_000, n_tf=1, cache_dir=None):
+        import pytorch_volumetric_b200 as pv
+        from pytorch_volumetric_b200 import distributed as pd
+        from pytorch_volumetric_b200.sdf import _sample_surface
+        v, f = workloads.bumpy_sphere(250, 101)
+        self.obj = pv.MeshObjectFactory("bumpy50k", mesh=(v, f))
+        surf = _sample_surface(self.obj, n_pts, 5, torch.device("cuda", torch.cuda.current_device())).float()
+        g = torch.Generator(device="cuda").manual_seed(5)
+        tf = workloads.random_rigid(1, seed=5, t_range=0.1).cuda()[0]
+        world_pts = surf @ tf[:3, :3].T + tf[:3, 3] + 0.002 * torch.randn(n_pts, 3, device="cuda", generator=g)
+        begin, end = pd.shard_range(n_pts, rank, world)
+        self.pts = world_pts[begin:end].contiguous()
+        self.host_pts = self.pts.cpu().pin_memory()
+        pert = workloads.random_rigid(n_tf, seed=6, t_range=0.01).cuda()
+        self.w2o = torch.linalg.inv(tf.unsqueeze(0)) @ pert
+        self.units = (end - begin) * n_tf
+        self.alg_bytes = 12 * (end - begin) + 48 * len(f) + 128 * self.obj._bvh_host[0].shape[0] + 4 * n_tf
+        self.h2d_bytes = 12 * (end - begin) + 64 * n_tf
+        self.d2h_bytes = 4 * n_tf
+        self.launches_per_step = 2
+        self.pv = pv
+        self.desc = {"workload": f"C5 chamfer: {n_pts}-point cloud -> 50 000-triangle bumpy sphere, B={n_tf} "
+                                 f"transform(s), cloud sharded over ranks", "points_this_rank": end - begin,
+                     "l2_policy": "60 MB cloud fits L2: L2 flushed between steps by a 256 MB memset"}
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step(self, i):
+        self.flush.zero_()
+        return self.pv.batch_chamfer_dist(self.w2o, self.pts, self.obj)
+
+    def step_host(self, i):
+        return self.pv.batch_chamfer_dist(self.w2o.cpu(), self.host_pts, self.obj)
+
+
+class C3(Workload):
+    """BASELINE C3: ComposedSDF of 16 drills (MeshSDF sharing one BVH) under random SE(3), 126^3 grid points."""
+    name = "c3"
+    kernel = "composed_query_kernel<true>"
+
+    def __init__(self, rank, world=1, cache_dir=None, cached=False):
+        import pytorch_volumetric_b200 as pv
+        v, f = workloads.fixture_mesh("drill")
+        obj = pv.MeshObjectFactory("drill", mesh=(v, f))
+        gt = pv.MeshSDF(obj)
+        if cached:
+            sub = pv.CachedSDF("drill", 0.005, obj.bounding_box(padding=0.1), gt, device="cuda",
+                               cache_path=os.path.join(cache_dir or tempfile.gettempdir(), f"pvb_c3_{rank}.pkl"))
+        else:
+            sub = gt
+        tm = workloads.random_rigid(16, seed=1, t_range=0.5).cuda()
+        self.comp = pv.ComposedSDF([sub] * 16, pv.Transform3d(matrix=tm))
+        axis = torch.arange(126, dtype=torch.float32) * (1.4 / 125) - 0.7
+        pts = torch.cartesian_prod(axis, axis, axis)
+        from pytorch_volumetric_b200 import distributed as pd
+        b, e = pd.shard_range(len(pts), rank, world)
+        self.host_pts = pts[b:e].contiguous().pin_memory()
+        self.pts = self.host_pts.cuda()
+        self.units = e - b
+        self.alg_bytes = 28 * self.units
+        self.h2d_bytes = 12 * self.units
+        self.d2h_bytes = 16 * self.units
+        self.launches_per_step = 1
+        self.desc = {"workload": f"C3 ComposedSDF of 16 drills ({'CachedSDF res=0.005' if cached else 'MeshSDF, one shared BVH'}) "
+                                 f"random SE(3), 126^3 grid points + gradient", "points_this_rank": self.units,
+                     "l2_policy": "L2 flushed between steps by a 256 MB memset"}
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+        if cached:
+            self.kernel = "composed_query_kernel<false>"
+
+    def step(self, i):
+        self.flush.zero_()
+        return self.comp(self.pts)
+
+    def step_host(self, i):
+        return self.comp(self.host_pts)
+
+
+def make_workload(name, rank, world):
+    if name == "c2":
+        return C2(rank)
+    if name == "mesh10k":
+        return Mesh10k(rank)
+    if name == "mesh50k":
+        return Mesh10k(rank, n_lon=250, n_lat=101)
+    if name == "c4":
+        return C4(rank, world)
+    if name == "c4readme":
+        return C4(rank, world, n_cfg=200, n_pts=15251)
+    if name == "c5":
+        return C5(rank, world)
+    if name == "c3":
+        return C3(rank, world)
+    if name == "c3cached":
+        return C3(rank, world, cached=True)
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    if args.workload not in ("c2", "mesh10k", "mesh50k"):
+        print(json.dumps({"impl": "reference", "unavailable": f"CPU arm implemented for c2 / mesh10k, not {args.workload}"}))
+        return 0
+    # The CPU arm needs the same tables as the GPU arm.  They are rebuilt on the host with the oracle's BVH
+    # evaluator (no GPU involvement), untimed.
+    from oracle import port, tp_open3d, _geom
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = max(torch.get_num_threads(), _geom.num_threads())
+    if args.workload == "c2":
+        tp_open3d.QUERY_METHOD = "bvh"
+        v, f = workloads.fixture_mesh("drill")
+        mesh = port.MeshPort(vertices=v, faces=f, name="drill")
+        np.random.seed(0)
+        sdf = port.CachedSDFPort("drill", 0.005, mesh.bounding_box(padding=0.1), port.MeshSDFPort(mesh))
+        lo = np.array([r[0] for r in sdf.ranges]); hi = np.array([r[1] for r in sdf.ranges])
+        sample = 2_000_000
+        pts = workloads.uniform_points(sample, lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo), seed=0)
+        fn = lambda: sdf(pts)
+        what = "oracle/port.py CachedSDFPort (op-for-op torch-cpu restatement of sdf.py:535-571)"
+        wl = "C2 CachedSDF(drill, res=0.005) value+gradient"
+    else:
+        tp_open3d.QUERY_METHOD = "bvh"
+        nl = (100, 51) if args.workload == "mesh10k" else (250, 101)
+        v, f = workloads.bumpy_sphere(*nl)
+        mesh = port.MeshPort(vertices=v, faces=f)
+        sample = 400_000
+        pts = workloads.uniform_points(sample, v.min(0) - 0.05, v.max(0) + 0.05, seed=2)
+        fn = lambda: mesh.closest_point(pts)
+        what = "oracle MeshPort.closest_point over the OpenMP BVH evaluator (sdf.py:122-172 restated)"
+        wl = f"MeshSDF on {len(f)}-triangle bumpy sphere"
+    for _ in range(max(args.warmup, 1)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl, "sample_points_per_step": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} points per step; {what}; host threads {cores}"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# -------------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = dist_setup(args.gpus)
+    wl = make_workload(args.workload, rank, world)
+    torch.cuda.synchronize()
+
+    # ---- device-resident arm (value) ----
+    for i in range(args.warmup):
+        wl.step(i)
+    stream = torch.cuda.current_stream()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    barrier(world)
+    sampler.start()
+    t_begin.record(stream)
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        out = wl.step(i)
+        ev[i][1].record(stream)
+    t_end.record(stream)
+    barrier(world)
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(t_begin.elapsed_time(t_end), world)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    kernel_ms = statistics.mean(step_ms)
+    units_all = max_over_ranks(float(wl.units), world) * world if args.workload in ("c2", "mesh10k", "mesh50k") \
+        else sum_over_ranks(float(wl.units), world)
+    value = units_all * args.steps / (total_ms * 1e-3)
+    del out
+
+    # ---- end-to-end arm: host buffers through the public API, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 10))
+        for i in range(2):
+            wl.step_host(i)
+        barrier(world)
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            r = wl.step_host(i)
+        torch.cuda.synchronize()
+        barrier(world)
+        dt = max_over_ranks(time.perf_counter() - t0, world)
+        e2e = {"value": units_all * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
+               "d2h_bytes_per_step": wl.d2h_bytes, "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps}
+        del r
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_kind = measured_peaks()
+    achieved = wl.alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(wl.name), "kernel": wl.kernel, "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": wl.alg_bytes, "peak_source": f"of {peak_kind}"}
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and hasattr(wl, "cpu_setup"):
+        from oracle import _geom
+        torch.set_num_threads(os.cpu_count() or 1)
+        sample = wl.cpu_setup()
+        wl.cpu_step()
+        t0 = time.perf_counter()
+        done = 0
+        while time.perf_counter() - t0 < 8.0:
+            done += wl.cpu_step()
+        dt = time.perf_counter() - t0
+        cpu = {"value": done / dt, "unit": UNIT, "cores": max(torch.get_num_threads(), _geom.num_threads()),
+               "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak" if args.workload in ("c2", "mesh10k", "mesh50k") else "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.desc, "clocks": clocks,
+                "e2e": e2e, "gpu_launches": wl.launches_per_step * args.steps, "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def sum_over_ranks(x, world):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+    return x
+
+
+if __name__ == "__main__":
+    sys.exit(main())

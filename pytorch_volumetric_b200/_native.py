@@ -173,6 +173,23 @@ def as_f32_points(points, device):
     return p.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
 
 
+def deliver(t, device, dtype=None):
+    """Move a result to the caller's device/dtype.  GPU -> host goes through pinned memory from torch's caching
+    host allocator (an asynchronous copy on the current stream followed by one stream sync), which is what makes
+    the host-buffer path run at PCIe speed instead of pageable-copy speed."""
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    device = torch.device(device)
+    if t.device == device:
+        return t
+    if device.type == "cpu" and t.device.type == "cuda":
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return out
+    return t.to(device)
+
+
 def bvh_build(verts32, faces32):
     """Host BVH4 build.  Returns (nodes uint8[n_nodes,128], tris float32[F,12], max_depth)."""
     L = lib()

@@ -72,7 +72,7 @@ def batch_chamfer_dist(world_to_object: torch.tensor, model_points_world_frame_e
             nat.check(L.pvb_chamfer(ctypes.byref(desc), nat.ptr(W[done:]), nb, nat.ptr(p), n, float(scale),
                                     nat.ptr(ws), nat.ptr(out[done:]), nat.stream_ptr(dev)), "pvb_chamfer")
             done += nb
-    return out.to(device=out_device, dtype=out_dtype)
+    return nat.deliver(out, out_device, out_dtype)
 
 
 def pairwise_distance_chamfer(A_link_to_world_tfs, B_world_to_link_tfs=None,

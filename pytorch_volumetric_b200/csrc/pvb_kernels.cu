@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -403,10 +404,25 @@ static int grid_for(long long work_items, int threads, int blocks_per_sm) {
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
-// shared-memory budget for the staged top of the tree
+// shared-memory budget for the staged top of the tree (PVB_STAGE_NODES overrides, for tuning)
+constexpr int kStageNodesMax = 1536;   // 192 KB
 static int stage_nodes_for(int n_nodes) {
-    const int max_nodes = 384;   // 48 KB
+    static int max_nodes = -1;
+    if (max_nodes < 0) {
+        max_nodes = 448;   // 56 KB: leaves most of the 228 KB carve-out to L1 for the deeper nodes and the stacks
+        if (const char *e = getenv("PVB_STAGE_NODES")) {
+            const int v = atoi(e);
+            if (v >= 0 && v <= kStageNodesMax) max_nodes = v;
+        }
+    }
     return n_nodes < max_nodes ? n_nodes : max_nodes;
+}
+
+// kernels that take the staged nodes as dynamic shared memory need the opt-in above 48 KB
+template <typename K>
+static bool allow_big_smem(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageNodesMax * 128) ==
+           cudaSuccess;
 }
 
 }  // namespace pvb
@@ -440,6 +456,11 @@ extern "C" int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_
     if (n == 0) return PVB_OK;
     const int n_stage = stage_nodes_for(mesh->n_nodes);
     const size_t smem = (size_t)n_stage * 128;
+    static const bool smem_ok = allow_big_smem(mesh_query_kernel);
+    if (!smem_ok) {
+        pvb_set_error("pvb_mesh_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+        return PVB_ERR_CUDA;
+    }
     const int blocks = grid_for(n, kMeshThreads, 8);
     mesh_query_kernel<<<blocks, kMeshThreads, smem, (cudaStream_t)stream>>>(*mesh, pts, n, mode, n_stage, out_dist,
                                                                             out_grad, out_closest, out_face, out_normal);
@@ -542,6 +563,11 @@ extern "C" int pvb_chamfer(const pvb_sdf_desc *obj, const float *world_to_object
     }
     const int n_blk = (int)pvb_chamfer_workspace(n_pts);
     const int n_stage = obj->kind == PVB_KIND_MESH ? stage_nodes_for(obj->n_nodes) : 0;
+    static const bool smem_ok = allow_big_smem(chamfer_partial_kernel);
+    if (!smem_ok) {
+        pvb_set_error("pvb_chamfer: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+        return PVB_ERR_CUDA;
+    }
     dim3 grid((unsigned)n_blk, (unsigned)n_tf);
     chamfer_partial_kernel<<<grid, kChamThreads, (size_t)n_stage * 128, (cudaStream_t)stream>>>(
         *obj, world_to_object, pts, n_pts, scale, n_stage, workspace);

@@ -236,7 +236,7 @@ class ObjectFactory(abc.ABC):
                       "pvb_mesh_query")
 
         def fin(t, tail):
-            return t.to(device=out_device, dtype=dtype).reshape(*lead, *tail)
+            return nat.deliver(t, out_device, dtype).reshape(*lead, *tail)
 
         return (fin(closest, (3,)), fin(dist, ()), fin(grad, (3,)),
                 fin(normal, (3,)) if compute_normal else None)
@@ -314,7 +314,7 @@ class ObjectFrameSDF(abc.ABC):
 def _result_like(points, lead, tensors_tails, out_device=None):
     dtype = points.dtype if torch.is_tensor(points) and points.dtype.is_floating_point else torch.float
     dev = out_device if out_device is not None else (points.device if torch.is_tensor(points) else torch.device("cpu"))
-    return tuple(t.to(device=dev, dtype=dtype).reshape(*lead, *tail) for t, tail in tensors_tails)
+    return tuple(nat.deliver(t, dev, dtype).reshape(*lead, *tail) for t, tail in tensors_tails)
 
 
 class SphereSDF(ObjectFrameSDF):
@@ -520,8 +520,8 @@ class ComposedSDF(ObjectFrameSDF):
         vv, gg = self.query(points_in_object_frame)
         dtype = points_in_object_frame.dtype if torch.is_tensor(points_in_object_frame) else torch.float
         out_device = points_in_object_frame.device if torch.is_tensor(points_in_object_frame) else "cpu"
-        vv = vv.to(device=out_device, dtype=dtype)
-        gg = gg.to(device=out_device, dtype=dtype)
+        vv = nat.deliver(vv, out_device, dtype)
+        gg = nat.deliver(gg, out_device, dtype)
         if self.tsf_batch is not None:
             # configuration batch dims first, then the query points' batch dims (sdf.py:428-431)
             vv = vv.reshape(*self.tsf_batch, *pts_shape[:-1])
@@ -727,21 +727,21 @@ class CachedSDF(ObjectFrameSDF):
             val_gt = self._fallback_sdf_value_func(p)
             assert torch.all((torch.abs(val - val_gt) < self.resolution)[inb])
         dtype = points_in_object_frame.dtype if torch.is_tensor(points_in_object_frame) else torch.float
-        return (val.to(device=self.device, dtype=dtype).reshape(lead),
-                grad.to(device=self.device, dtype=dtype).reshape(*lead, 3))
+        return (nat.deliver(val, self.device, dtype).reshape(lead),
+                nat.deliver(grad, self.device, dtype).reshape(*lead, 3))
 
     def outside_surface(self, points_in_object_frame, surface_level=0):
         lead = tuple(points_in_object_frame.shape[:-1])
         _, _, _, outside, _ = self._lookup(points_in_object_frame, want_val=False, want_outside=True,
                                            surface_level=surface_level)
-        return outside.to(device=self.device, dtype=torch.bool).reshape(lead)
+        return nat.deliver(outside, self.device, torch.bool).reshape(lead)
 
     def voxel_keys(self, points_in_object_frame):
         """Ravelled nearest-voxel key per point (int64, -1 where out of the cached range): the index/occupancy
         quantity that must be bit-exact against the reference (sdf.py:537-540)."""
         lead = tuple(points_in_object_frame.shape[:-1])
         _, _, _, _, index = self._lookup(points_in_object_frame, want_val=False, want_index=True)
-        return index.to(device=self.device).reshape(lead)
+        return nat.deliver(index, self.device).reshape(lead)
 
     def get_voxel_view(self, voxels: VoxelGrid = None, dtype=torch.float, device='cpu') -> GridView:
         if voxels is None:

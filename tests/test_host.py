@@ -1,0 +1,242 @@
+"""CPU: host-side logic of the product -- C ABI surface, BVH builder invariants, API mirrors, sharding."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol(built_lib):
+    from pytorch_volumetric_b200 import _native
+    header = open(os.path.join(ROOT, "include", "pvb.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pvb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(_native.LIB_PATH)
+    for sym in declared:
+        assert hasattr(raw, sym), f"{sym} declared in include/pvb.h but not exported by libpvb.so"
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    assert built_lib.pvb_sizeof_sdf_desc() == ctypes.sizeof(_native.SdfDesc)
+    assert built_lib.pvb_sizeof_bvh4_node() == 128
+    assert built_lib.pvb_version() == 100
+
+
+def test_c_abi_argument_validation_without_gpu(built_lib):
+    from pytorch_volumetric_b200 import _native
+    d = _native.SdfDesc()
+    rc = built_lib.pvb_mesh_query(ctypes.byref(d), None, 10, 3, None, None, None, None, None, None)
+    assert rc == -1 and b"null" in built_lib.pvb_last_error()
+    rc = built_lib.pvb_grid_lookup(ctypes.byref(d), ctypes.c_void_p(16), 10, None, None, None, 0.0, None, None)
+    assert rc == -1 and b"empty" in built_lib.pvb_last_error()
+    v = np.zeros((3, 3), np.float32)
+    f = np.array([[0, 1, 5]], np.int32)
+    with pytest.raises(_native.NativeLibraryError, match="out of range"):
+        _native.bvh_build(v, f)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """The product path must fail loudly, not fall back, when there is no CUDA device."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import pytorch_volumetric_b200 as pv
+    from pytorch_volumetric_b200._native import NativeLibraryError
+    v, f = workloads.fixture_mesh("probe")
+    obj = pv.MeshObjectFactory("probe", mesh=(v, f))
+    with pytest.raises(NativeLibraryError, match="no CPU fallback"):
+        pv.MeshSDF(obj)(torch.zeros(4, 3))
+    with pytest.raises(NativeLibraryError):
+        pv.SphereSDF(1.0)(torch.zeros(4, 3))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pytorch_volumetric_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+                assert "liborc_geom" not in src, fn
+
+
+@pytest.mark.parametrize("name", ["probe", "wrench", "drill"])
+def test_bvh_builder_invariants(name, built_lib):
+    from pytorch_volumetric_b200 import _native
+    v, f = workloads.fixture_mesh(name)
+    v32 = v.astype(np.float32)
+    nodes_raw, tris, depth = _native.bvh_build(v32, f)
+    nodes = nodes_raw.view(np.float32).reshape(-1, 32)
+    child = nodes_raw.view(np.int32).reshape(-1, 32)[:, 24:28]
+    n_nodes = len(nodes)
+    assert 3 * depth + 2 <= 40
+    face_of = tris.view(np.int32)[:, 3]
+    assert np.array_equal(np.sort(face_of), np.arange(len(f)))        # a permutation of the faces
+    assert np.array_equal(tris[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]].reshape(-1, 3, 3), v32[f[face_of]])
+    seen_tri = np.zeros(len(f), dtype=int)
+    seen_node = np.zeros(n_nodes, dtype=int)
+    seen_node[0] = 1
+
+    def box(node, k):
+        return nodes[node, [0 + k, 4 + k, 8 + k]], nodes[node, [12 + k, 16 + k, 20 + k]]
+
+    def node_bounds(i):
+        los, his = [], []
+        for k in range(4):
+            if child[i, k] != -2 ** 31:
+                lo, hi = box(i, k)
+                los.append(lo); his.append(hi)
+        return np.min(los, axis=0), np.max(his, axis=0)
+
+    for i in range(n_nodes):
+        for k in range(4):
+            c = int(child[i, k])
+            if c == -2 ** 31:
+                continue
+            lo, hi = box(i, k)
+            if c >= 0:
+                assert c > i, "BFS layout: children come after their parent"
+                seen_node[c] += 1
+                clo, chi = node_bounds(c)
+                assert (clo >= lo).all() and (chi <= hi).all()
+            else:
+                code = ~c
+                first, cnt = code >> 2, (code & 3) + 1
+                seen_tri[first:first + cnt] += 1
+                tv = tris[first:first + cnt][:, [0, 1, 2, 4, 5, 6, 8, 9, 10]].reshape(-1, 3)
+                assert (tv >= lo).all() and (tv <= hi).all()
+    assert (seen_tri == 1).all() and (seen_node == 1).all()
+
+
+def test_grid_helpers_match_port():
+    import pytorch_volumetric_b200 as pv
+    from oracle import port
+    rng = np.array([[-0.067981, 0.095006], [-0.041332, 0.081863], [-0.003716, 0.183718]])
+    rng[:, 0] -= 0.1; rng[:, 1] += 0.1
+    for res in (0.005, 0.01, 0.02):
+        a = pv.get_divisible_range_by_resolution(res, rng)
+        b = port.divisible_range(res, rng)
+        assert a == b
+        ca, pa = pv.get_coordinates_and_points_in_grid(res, a)
+        cb, pb = port.grid_coords_and_points(res, b)
+        assert all(torch.equal(x, y) for x, y in zip(ca, cb)) and torch.equal(pa, pb)
+    assert [len(c) for c in pv.get_coordinates_and_points_in_grid(0.005, pv.get_divisible_range_by_resolution(0.005, rng))[0]] == [74, 66, 78]
+
+
+def test_transform3d_and_kinematics_match_oracle_restatement(tmp_path):
+    import pytorch_volumetric_b200 as pv
+    from oracle import tp_pytorch_kinematics as opk
+    m = workloads.random_rigid(7, seed=2)
+    a, b = pv.Transform3d(matrix=m), opk.Transform3d(matrix=m)
+    p = torch.randn(50, 3)
+    assert torch.allclose(a.transform_points(p), b.transform_points(p), atol=1e-6)
+    assert torch.allclose(a.inverse().get_matrix(), b.inverse().get_matrix(), atol=1e-6)
+    assert torch.allclose(a.transform_normals(p), b.transform_normals(p), atol=1e-5)
+    assert torch.allclose(a[2:5].get_matrix(), b[2:5].get_matrix())
+    assert torch.allclose(a.compose(a.inverse()).get_matrix(), torch.eye(4).repeat(7, 1, 1), atol=1e-6)
+    assert a[0].transform_points(p).shape == (50, 3) and a.transform_points(p).shape == (7, 50, 3)
+    t = pv.Translate(0.1, 0, 0).stack(pv.Translate(-0.2, 0, 0.2))
+    assert len(t) == 2 and torch.allclose(t.get_matrix()[1, :3, 3], torch.tensor([-0.2, 0.0, 0.2]))
+    urdf, end = workloads.write_arm(str(tmp_path))
+    data = open(urdf).read()
+    c1 = pv.build_serial_chain_from_urdf(data, end)
+    c2 = opk.build_serial_chain_from_urdf(data, end)
+    assert c1.get_joint_parameter_names() == c2.get_joint_parameter_names()
+    assert c1.get_frame_names(exclude_fixed=False) == c2.get_frame_names(exclude_fixed=False)
+    th = workloads.arm_configurations(6)
+    f1 = c1.forward_kinematics(th, end_only=False)
+    f2 = c2.forward_kinematics(th, end_only=False)
+    for k in f2:
+        assert torch.allclose(f1[k].get_matrix(), f2[k].get_matrix(), atol=2e-6), k
+    vis = c1.find_frame("link_3").link.visuals[0]
+    assert vis.geom_type == "mesh" and vis.geom_param[0] == "link.obj" and vis.geom_param[1] == [3.0, 3.0, 3.0]
+
+
+def test_mesh_factory_host_side(tmp_path):
+    import pytorch_volumetric_b200 as pv
+    from pytorch_volumetric_b200.meshio import write_obj
+    from oracle import port
+    v, f = workloads.fixture_mesh("probe")
+    path = str(tmp_path / "probe.obj")
+    write_obj(path, v, f)
+    kw = dict(scale=2.0, vis_frame_pos=(0.01, 0.02, 0.03), vis_frame_rot=(0.1, 0.2, 0.3, 0.9))
+    obj = pv.MeshObjectFactory(path, **kw)
+    ref = port.MeshPort(path, **kw)
+    np.testing.assert_allclose(obj._mesh.vertices, ref.mesh.vertices, atol=1e-15)
+    np.testing.assert_allclose(obj.bounding_box(0.1, 0.05), ref.bounding_box(0.1, 0.05), atol=1e-15)
+    np.testing.assert_allclose(obj._face_normals, ref.face_normals, atol=1e-12)
+    np.testing.assert_allclose(obj.center(), ref.mesh.get_center(), atol=1e-15)
+    with pytest.raises(RuntimeError, match="does not exist"):
+        pv.MeshObjectFactory(str(tmp_path / "missing.obj"))
+    pre = pv.MeshObjectFactory("package://probe.obj", path_prefix=str(tmp_path))
+    assert pre.get_mesh_resource_filename() == path
+    import pickle
+    again = pickle.loads(pickle.dumps(obj))
+    np.testing.assert_array_equal(again._mesh.vertices, obj._mesh.vertices)
+    assert pv.MeshSDF(obj).surface_bounding_box(padding=0.1).shape == (3, 2)
+
+
+def test_shard_range_and_gather_single_process():
+    from pytorch_volumetric_b200.distributed import shard_range, all_gather_slabs
+    for n in (0, 1, 7, 200, 100003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    x = torch.arange(6.).reshape(3, 2)
+    assert all_gather_slabs(x, [3]) is x
+
+
+def _gloo_worker(rank, world, port_no, tmpdir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pytorch_volumetric_b200 import distributed as pd
+
+    class Sphere:                      # CPU stand-in for an ObjectFrameSDF (host logic only)
+        def __call__(self, p):
+            r = p.norm(dim=-1)
+            return r - 1.0, p / r.unsqueeze(-1)
+
+    pts = torch.randn(2, 103, 3, generator=torch.Generator().manual_seed(0))
+    v, g = pd.sharded_query(Sphere(), pts, gather=True)
+    v_ref, g_ref = Sphere()(pts)
+    ok1 = torch.equal(v, v_ref) and torch.equal(g, g_ref)
+
+    class FakeComposed:                # the configuration-slab contract of ComposedSDF.query
+        tsf_batch = (5,)
+
+        def query(self, points, cfg_begin=0, cfg_count=None):
+            P = points.reshape(-1, 3).shape[0]
+            cfg = torch.arange(cfg_begin, cfg_begin + cfg_count, dtype=torch.float32)
+            val = (cfg[:, None] * 1000 + torch.arange(P)[None]).reshape(-1)
+            return val, val[:, None].repeat(1, 3)
+
+    class FakeRobot:
+        sdf = FakeComposed()
+
+    rv, rg = pd.sharded_robot_query(FakeRobot(), pts[0], gather=True)
+    exp = torch.arange(5.)[:, None] * 1000 + torch.arange(103.)[None]
+    ok2 = torch.equal(rv, exp) and rg.shape == (5, 103, 3)
+    lv, lg, (b, e) = pd.sharded_robot_query(FakeRobot(), pts[0], gather=False)
+    ok3 = (b, e) == pd.shard_range(5, rank, world) and lv.shape == (e - b, 103)
+    ragged = pd.all_gather_slabs(torch.full((rank + 1, 2), float(rank)), [1, 2])
+    ok4 = torch.equal(ragged, torch.tensor([[0., 0.], [1., 1.], [1., 1.]]))
+    with open(os.path.join(tmpdir, f"ok{rank}"), "w") as fh:
+        fh.write(str(int(ok1 and ok2 and ok3 and ok4)))
+    dist.destroy_process_group()
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port_no = s.getsockname()[1]; s.close()
+    mp.spawn(_gloo_worker, args=(2, port_no, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
