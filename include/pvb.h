@@ -58,7 +58,7 @@ enum {
 };
 
 /*
- * One queryable object.  224 bytes (pvb_sizeof_sdf_desc()), POD, host-resident (device pointers
+ * One queryable object.  232 bytes (pvb_sizeof_sdf_desc()), POD, host-resident (device pointers
  * inside); arrays of these are copied to the device by the caller for the
  * composed kernels.
  *
@@ -97,7 +97,11 @@ typedef struct pvb_sdf_desc {
     uint32_t ray_seed;          /* seed of the deterministic stand-in for sdf.py:149's jitter */
     /* ---- sphere ---- */
     float radius;
-    uint8_t _reserved[16];
+    /* ---- grid: fast index path ----
+     * k = rintf((p - min32) * inv_res32) is taken as the voxel index when |q - k| <= idx_certain (the fp32
+     * estimate provably rounds the same way as the exact formula); otherwise the exact formula above runs. */
+    float inv_res32[3];
+    float idx_certain[3];
 } pvb_sdf_desc;
 
 /* BVH4 node, 128 bytes: SoA child boxes + child links.

@@ -13,7 +13,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libpvb.so")
+LIB_PATH = os.environ.get("PVB_LIB") or os.path.join(CSRC, "libpvb.so")   # PVB_LIB: tuning builds only
 SOURCES = ["pvb_kernels.cu", "bvh_build.cpp"]
 HEADERS = ["pvb_device.cuh", os.path.join("..", "..", "include", "pvb.h")]
 
@@ -64,7 +64,7 @@ class SdfDesc(ctypes.Structure):
         ("n_nodes", ctypes.c_int32),
         ("nodes", ctypes.c_void_p), ("tris", ctypes.c_void_p), ("face_normals", ctypes.c_void_p),
         ("n_tris", ctypes.c_int32), ("ray_far", ctypes.c_float * 3), ("ray_seed", ctypes.c_uint32),
-        ("radius", ctypes.c_float), ("_reserved", ctypes.c_uint8 * 16),
+        ("radius", ctypes.c_float), ("inv_res32", ctypes.c_float * 3), ("idx_certain", ctypes.c_float * 3),
     ]
 
     def copy(self):

@@ -282,22 +282,31 @@ __device__ __forceinline__ SdfOut mesh_eval(const pvb_sdf_desc &m, const NodeSta
 // ----------------------------------------------------------------------------
 // CachedSDF: nearest-voxel index (TorchMultidimView.ensure_index_key semantics).
 // Returns the ravelled key, or -1 when the point fails all(min <= p <= max).
+// The reference formula, exactly (TorchMultidimView.ensure_index_key): round((p - min) / res), in fp64 when the
+// range came from numpy (torch.tensor of numpy scalars is float64) and in fp32 for Python-float ranges.
+// Out of line: it runs for ~0.03 % of the coordinates and must not cost the streaming path registers.
+__device__ __noinline__ float grid_axis_index_exact(float pv, double min64, double res64, float min32, float res32,
+                                                    bool fp32_mode) {
+    if (fp32_mode) return rintf(__fdiv_rn(pv - min32, res32));
+    return (float)rint(__ddiv_rn((double)pv - min64, res64));
+}
+
+__device__ __forceinline__ int grid_axis_index(const pvb_sdf_desc &g, int a, float pv) {
+    // fast path: fp32 estimate, accepted when it cannot round differently from the exact formula
+    const float q = (pv - g.min32[a]) * g.inv_res32[a];
+    float kf = rintf(q);
+    if (!(fabsf(q - kf) <= g.idx_certain[a]))   // inside the uncertainty band of a cell boundary
+        kf = grid_axis_index_exact(pv, g.min64[a], g.res64[a], g.min32[a], g.res32[a],
+                                   (g.flags & PVB_GRID_INDEX_FP32) != 0);
+    return min(max((int)kf, 0), g.dims[a] - 1);   // clamp: memory safety only
+}
+
 __device__ __forceinline__ long long grid_key(const pvb_sdf_desc &g, f3 p) {
     const bool inb = (p.x >= g.valid_lo[0]) & (p.x <= g.valid_hi[0]) & (p.y >= g.valid_lo[1]) &
                      (p.y <= g.valid_hi[1]) & (p.z >= g.valid_lo[2]) & (p.z <= g.valid_hi[2]);
     if (!inb) return -1;
-    int k[3];
-    const float pv[3] = {p.x, p.y, p.z};
-    if (g.flags & PVB_GRID_INDEX_FP32) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) k[a] = (int)rintf(__fdiv_rn(pv[a] - g.min32[a], g.res32[a]));
-    } else {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) k[a] = (int)rint(__ddiv_rn((double)pv[a] - g.min64[a], g.res64[a]));
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) k[a] = min(max(k[a], 0), g.dims[a] - 1);   // memory safety only
-    return ((long long)k[0] * g.dims[1] + k[1]) * g.dims[2] + k[2];
+    const int k0 = grid_axis_index(g, 0, p.x), k1 = grid_axis_index(g, 1, p.y), k2 = grid_axis_index(g, 2, p.z);
+    return (long long)((k0 * g.dims[1] + k1) * g.dims[2] + k2);   // < 2^31 voxels, checked by the ABI
 }
 
 // Point-to-AABB rule for out-of-range points (sdf.py:555-571).

@@ -136,40 +136,71 @@ mesh_query_kernel(const pvb_sdf_desc m, const float *__restrict__ pts, long long
 // the table (16 B/voxel, interleaved {val,gx,gy,gz}) stays L2 resident.
 constexpr int kGridThreads = 256;
 
-// 4 points per thread: three 128-bit loads cover 4 xyz triples, results leave
-// as one float4 of values and three float4 of gradients.
+// 4 points per thread and per quad: three 128-bit loads cover 4 xyz triples, results leave as one float4 of values
+// and three float4 of gradients.  PVB_GRID_UNROLL quads are in flight per thread (all loads issued before any
+// dependent work) so that enough bytes are outstanding to cover HBM latency at the occupancy the register count
+// allows.
+#ifndef PVB_GRID_UNROLL
+#define PVB_GRID_UNROLL 2
+#endif
+#ifndef PVB_GRID_MINB
+#define PVB_GRID_MINB 4
+#endif
+
 template <bool kMesh>
-__global__ void __launch_bounds__(kGridThreads)
+__device__ __forceinline__ void grid_quad(const pvb_sdf_desc &g, const NodeStage &st, long long t, float4 a, float4 b,
+                                          float4 c, uint32_t mesh_mode, float4 *__restrict__ out_val4,
+                                          float4 *__restrict__ out_grad4, uchar4 *__restrict__ out_outside4,
+                                          float surface_level, longlong2 *__restrict__ out_index2) {
+    const f3 p[4] = {mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w)};
+    SdfOut o[4];
+    long long key[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = grid_eval<kMesh>(g, st, p[k], mesh_mode, (uint64_t)(4 * t + k), &key[k]);
+    if (out_val4) __stcs(out_val4 + t, make_float4(o[0].val, o[1].val, o[2].val, o[3].val));
+    if (out_grad4) {
+        __stcs(out_grad4 + 3 * t, make_float4(o[0].grad.x, o[0].grad.y, o[0].grad.z, o[1].grad.x));
+        __stcs(out_grad4 + 3 * t + 1, make_float4(o[1].grad.y, o[1].grad.z, o[2].grad.x, o[2].grad.y));
+        __stcs(out_grad4 + 3 * t + 2, make_float4(o[2].grad.z, o[3].grad.x, o[3].grad.y, o[3].grad.z));
+    }
+    if (out_outside4) {   // outside_surface: out of range => outside (sdf.py:600-601)
+        uchar4 m;
+        m.x = key[0] < 0 ? 1 : (o[0].val > surface_level);
+        m.y = key[1] < 0 ? 1 : (o[1].val > surface_level);
+        m.z = key[2] < 0 ? 1 : (o[2].val > surface_level);
+        m.w = key[3] < 0 ? 1 : (o[3].val > surface_level);
+        out_outside4[t] = m;
+    }
+    if (out_index2) {
+        out_index2[2 * t] = make_longlong2(key[0], key[1]);
+        out_index2[2 * t + 1] = make_longlong2(key[2], key[3]);
+    }
+}
+
+template <bool kMesh>
+__global__ void __launch_bounds__(kGridThreads, PVB_GRID_MINB)
 grid_lookup_vec4_kernel(const pvb_sdf_desc g, const float4 *__restrict__ pts4, long long n_quads, uint32_t mesh_mode,
                         float4 *__restrict__ out_val4, float4 *__restrict__ out_grad4,
                         uchar4 *__restrict__ out_outside4, float surface_level, longlong2 *__restrict__ out_index2) {
     NodeStage st; st.smem = nullptr; st.n = 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_quads; t += stride) {
-        const float4 a = __ldcs(pts4 + 3 * t), b = __ldcs(pts4 + 3 * t + 1), c = __ldcs(pts4 + 3 * t + 2);
-        const f3 p[4] = {mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w)};
-        SdfOut o[4];
-        long long key[4];
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; t + (PVB_GRID_UNROLL - 1) * stride < n_quads; t += PVB_GRID_UNROLL * stride) {
+        float4 a[PVB_GRID_UNROLL], b[PVB_GRID_UNROLL], c[PVB_GRID_UNROLL];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = grid_eval<kMesh>(g, st, p[k], mesh_mode, (uint64_t)(4 * t + k), &key[k]);
-        if (out_val4) __stcs(out_val4 + t, make_float4(o[0].val, o[1].val, o[2].val, o[3].val));
-        if (out_grad4) {
-            __stcs(out_grad4 + 3 * t, make_float4(o[0].grad.x, o[0].grad.y, o[0].grad.z, o[1].grad.x));
-            __stcs(out_grad4 + 3 * t + 1, make_float4(o[1].grad.y, o[1].grad.z, o[2].grad.x, o[2].grad.y));
-            __stcs(out_grad4 + 3 * t + 2, make_float4(o[2].grad.z, o[3].grad.x, o[3].grad.y, o[3].grad.z));
+        for (int u = 0; u < PVB_GRID_UNROLL; ++u) {
+            const float4 *src = pts4 + 3 * (t + u * stride);
+            a[u] = __ldcs(src); b[u] = __ldcs(src + 1); c[u] = __ldcs(src + 2);
         }
-        if (out_outside4) {   // outside_surface: out of range => outside (sdf.py:600-601)
-            uchar4 m;
-            m.x = key[0] < 0 ? 1 : (o[0].val > surface_level);
-            m.y = key[1] < 0 ? 1 : (o[1].val > surface_level);
-            m.z = key[2] < 0 ? 1 : (o[2].val > surface_level);
-            m.w = key[3] < 0 ? 1 : (o[3].val > surface_level);
-            out_outside4[t] = m;
-        }
-        if (out_index2) {
-            out_index2[2 * t] = make_longlong2(key[0], key[1]);
-            out_index2[2 * t + 1] = make_longlong2(key[2], key[3]);
-        }
+#pragma unroll
+        for (int u = 0; u < PVB_GRID_UNROLL; ++u)
+            grid_quad<kMesh>(g, st, t + u * stride, a[u], b[u], c[u], mesh_mode, out_val4, out_grad4, out_outside4,
+                             surface_level, out_index2);
+    }
+    for (; t < n_quads; t += stride) {
+        const float4 *src = pts4 + 3 * t;
+        const float4 a = __ldcs(src), b = __ldcs(src + 1), c = __ldcs(src + 2);
+        grid_quad<kMesh>(g, st, t, a, b, c, mesh_mode, out_val4, out_grad4, out_outside4, surface_level, out_index2);
     }
 }
 
@@ -476,6 +507,10 @@ extern "C" int pvb_grid_lookup(const pvb_sdf_desc *grid, const float *pts, int64
     }
     if (!grid->table || grid->dims[0] < 1 || grid->dims[1] < 1 || grid->dims[2] < 1) {
         pvb_set_error("pvb_grid_lookup: grid part of the descriptor is empty");
+        return PVB_ERR_INVALID;
+    }
+    if ((long long)grid->dims[0] * grid->dims[1] * grid->dims[2] >= (1ll << 31)) {
+        pvb_set_error("pvb_grid_lookup: more than 2^31 voxels");
         return PVB_ERR_INVALID;
     }
     if (grid->flags & PVB_GRID_OOB_GT)

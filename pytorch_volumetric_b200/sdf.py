@@ -646,6 +646,15 @@ class CachedSDF(ObjectFrameSDF):
                 d.valid_lo[k], d.valid_hi[k] = float(_fp32_ceil(lo[k])), float(_fp32_floor(hi[k]))
             d.bb_min[k] = float(bb[k, 0])
             d.bb_max[k] = float(bb[k, 1])
+            # fast fp32 index estimate + the band around cell boundaries in which the exact formula is used
+            if shape[k] > 1 and math.isfinite(d.res64[k]) and d.res64[k] > 0:
+                d.inv_res32[k] = float(np.float32(1.0 / d.res64[k]))
+                scale = max(abs(lo[k]), abs(hi[k])) + (hi[k] - lo[k])
+                err = 4.0 * scale * 2.0 ** -24 / d.res64[k] + (shape[k] + 4) * 2.0 ** -22
+                d.idx_certain[k] = max(0.5 - (4.0 * err + 1e-6), -1.0)
+            else:
+                d.inv_res32[k] = 0.0
+                d.idx_certain[k] = -1.0          # always take the exact path
             if shape[k] > 1:
                 res_max = max(res_max, d.res64[k])
         gt_native = None

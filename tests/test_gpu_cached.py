@@ -129,10 +129,18 @@ def test_cached_c2_full_size_properties(tmp_path):
     # gather consistency: values are exactly table[key]
     assert torch.equal(val[inb], c.voxels.raw_data[keys[inb]])
     assert torch.equal(grad[inb], c.voxels_grad[keys[inb]])
-    # every voxel centre reads back its own cell (the reference's own self-check, sdf.py:509-512)
+    # every voxel centre reads back its own cell (the reference's own self-check, sdf.py:509-512); a centre on
+    # the upper face can round up in fp32 to just above the fp64 range end, which the reference's own
+    # all(min <= p <= max) test then calls out of range -- the oracle decides
+    from oracle import port
     coords, centres = pv.get_coordinates_and_points_in_grid(0.005, c.ranges)
-    kc = c.voxel_keys(centres.cuda())
-    assert torch.equal(kc.cpu(), torch.arange(len(centres)))
+    kc = c.voxel_keys(centres.cuda()).cpu()
+    ref = port.CachedSDFPort("drill", 0.005, obj.bounding_box(padding=0.1), port.SphereSDFPort(1.0),
+                             tables=(c.voxels.raw_data.cpu().reshape(tuple(c.voxels.shape)), c.voxels_grad.cpu()))
+    _, flat, inb_ref = ref.index_and_mask(centres)
+    assert torch.equal(kc >= 0, inb_ref) and torch.equal(kc[inb_ref], flat[inb_ref])
+    assert torch.equal(kc[inb_ref], torch.arange(len(centres))[inb_ref])
+    assert inb_ref.float().mean() > 0.9
     # vectorised (4 points / thread) and scalar kernels agree bit-for-bit: a view offset by one point is not
     # 16-byte aligned and takes the scalar kernel
     v2, g2 = c(q[1:1_000_001])
