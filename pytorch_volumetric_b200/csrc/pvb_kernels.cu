@@ -79,6 +79,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Stage the first n_stage BVH nodes (BFS prefix = top of the tree) into shared
 // memory with one bulk asynchronous copy; every thread then waits on the mbarrier.
 __device__ __forceinline__ NodeStage stage_nodes(const void *gnodes, int n_nodes, int n_stage_max,
@@ -202,6 +214,86 @@ grid_lookup_vec4_kernel(const pvb_sdf_desc g, const float4 *__restrict__ pts4, l
         const float4 a = __ldcs(src), b = __ldcs(src + 1), c = __ldcs(src + 2);
         grid_quad<kMesh>(g, st, t, a, b, c, mesh_mode, out_val4, out_grad4, out_outside4, surface_level, out_index2);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-streamed variant (the C2 headline path).  Random table gathers cost ~2 L1 wavefront-cycles per lane and
+// cannot be coalesced, so the LSU is the scarce resource of this kernel; the AoS point / gradient streams (48-byte
+// lane stride = 12 cache lines per warp instruction) would spend as much LSU time again.  They are therefore
+// moved by the bulk-copy engine instead: one cp.async.bulk brings a tile of TILE points into shared memory
+// (double buffered, mbarrier completion), threads read their 4 points with three conflict-free LDS.128, results
+// are staged in shared memory and leave with cp.async.bulk shared->global stores (bulk groups).  The LSU then
+// only executes the gathers.
+constexpr int kTmaThreads = 256;
+constexpr int kTmaTile = kTmaThreads * 4;              // points per tile
+struct __align__(128) GridTmaSmem {
+    float in[2][kTmaTile * 3];                         // 2 x 12 KB
+    float outv[2][kTmaTile];                           // 2 x  4 KB
+    float outg[2][kTmaTile * 3];                       // 2 x 12 KB
+    uint64_t full[2];
+};
+
+__global__ void __launch_bounds__(kTmaThreads)
+grid_lookup_tma_kernel(const pvb_sdf_desc g, const float *__restrict__ pts, long long n_pts /* multiple of 4 */,
+                       float *__restrict__ out_val, float *__restrict__ out_grad) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    GridTmaSmem &s = *reinterpret_cast<GridTmaSmem *>(smem_raw);
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    const long long n_tiles = (n_pts + kTmaTile - 1) / kTmaTile;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&s.full[0], 1);
+        mbar_init(&s.full[1], 1);
+    }
+    __syncthreads();
+    auto tile_points = [&](long long tile) -> uint32_t {
+        const long long left = n_pts - tile * kTmaTile;
+        return (uint32_t)(left < kTmaTile ? left : kTmaTile);
+    };
+    long long tile = blockIdx.x;
+    if (tid == 0 && tile < n_tiles) {
+        const uint32_t bytes = tile_points(tile) * 12u;
+        mbar_expect_tx(&s.full[0], bytes);
+        bulk_g2s(s.in[0], pts + tile * kTmaTile * 3, bytes, &s.full[0]);
+    }
+    for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+        const int buf = it & 1;
+        const long long next = tile + gridDim.x;
+        if (tid == 0 && next < n_tiles) {      // in[buf^1] was released by the __syncthreads of the previous iteration
+            const uint32_t bytes = tile_points(next) * 12u;
+            mbar_expect_tx(&s.full[buf ^ 1], bytes);
+            bulk_g2s(s.in[buf ^ 1], pts + next * kTmaTile * 3, bytes, &s.full[buf ^ 1]);
+        }
+        mbar_wait(&s.full[buf], (uint32_t)((it >> 1) & 1));
+        const uint32_t npt = tile_points(tile);
+        const bool active = (uint32_t)(4 * tid) < npt;
+        SdfOut o[4];
+        if (active) {
+            const float4 *src = reinterpret_cast<const float4 *>(s.in[buf]) + 3 * tid;
+            const float4 a = src[0], b = src[1], c = src[2];
+            const f3 p[4] = {mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = grid_eval<false>(g, st, p[k], 0u, 0ull, nullptr);
+        }
+        // out[buf] was handed to the bulk-store engine two iterations ago: wait until it has been read
+        if (tid == 0) bulk_wait_read<1>();
+        __syncthreads();
+        if (active) {
+            reinterpret_cast<float4 *>(s.outv[buf])[tid] = make_float4(o[0].val, o[1].val, o[2].val, o[3].val);
+            float4 *dg = reinterpret_cast<float4 *>(s.outg[buf]) + 3 * tid;
+            dg[0] = make_float4(o[0].grad.x, o[0].grad.y, o[0].grad.z, o[1].grad.x);
+            dg[1] = make_float4(o[1].grad.y, o[1].grad.z, o[2].grad.x, o[2].grad.y);
+            dg[2] = make_float4(o[2].grad.z, o[3].grad.x, o[3].grad.y, o[3].grad.z);
+        }
+        fence_async_smem();       // generic-proxy smem writes -> visible to the async (bulk copy) proxy
+        __syncthreads();          // also releases in[buf] for the load issued in the next iteration
+        if (tid == 0) {
+            bulk_s2g(out_val + tile * kTmaTile, s.outv[buf], npt * 4u);
+            bulk_s2g(out_grad + tile * kTmaTile * 3, s.outg[buf], npt * 12u);
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_read<0>();
 }
 
 // scalar variant for the tail and for unaligned views
@@ -521,8 +613,24 @@ extern "C" int pvb_grid_lookup(const pvb_sdf_desc *grid, const float *pts, int64
     auto aligned = [](const void *p, size_t a) { return p == nullptr || ((uintptr_t)p % a) == 0; };
     const bool vec_ok = aligned(pts, 16) && aligned(out_val, 16) && aligned(out_grad, 16) && aligned(out_outside, 4) &&
                         aligned(out_index, 16);
-    const long long n_quads = vec_ok ? n / 4 : 0;
-    if (n_quads > 0) {
+    long long n_quads = vec_ok ? n / 4 : 0;
+    static const int use_tma = [] { const char *e = getenv("PVB_GRID_TMA"); return e ? atoi(e) : 1; }();
+    if (use_tma && n_quads >= 4 * kTmaTile && !gt && out_val && out_grad && !out_outside && !out_index) {
+        static const bool smem_ok = cudaFuncSetAttribute(grid_lookup_tma_kernel,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)sizeof(GridTmaSmem)) == cudaSuccess;
+        if (!smem_ok) {
+            pvb_set_error("pvb_grid_lookup: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+            return PVB_ERR_CUDA;
+        }
+        static const int ctas_per_sm = [] { const char *e = getenv("PVB_GRID_TMA_CTAS"); return e ? atoi(e) : 3; }();
+        const long long n_tiles = (4 * n_quads + kTmaTile - 1) / kTmaTile;
+        const long long cap = (long long)sm_count() * ctas_per_sm;
+        const int blocks = (int)(n_tiles < cap ? n_tiles : cap);
+        grid_lookup_tma_kernel<<<blocks, kTmaThreads, sizeof(GridTmaSmem), (cudaStream_t)stream>>>(
+            *grid, pts, 4 * n_quads, out_val, out_grad);
+        PVB_CHECK_LAUNCH("pvb_grid_lookup(tma)");
+    } else if (n_quads > 0) {
         const int blocks = grid_for(n_quads, kGridThreads, 8);
         auto kern = gt ? grid_lookup_vec4_kernel<true> : grid_lookup_vec4_kernel<false>;
         kern<<<blocks, kGridThreads, 0, (cudaStream_t)stream>>>(

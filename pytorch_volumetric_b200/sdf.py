@@ -809,7 +809,7 @@ def sample_mesh_points(obj_factory: ObjectFactory = None, num_points=100, seed=0
     return points.to(device=device, dtype=dtype), normals.to(device=device, dtype=dtype), cache
 
 
-def _sample_surface(obj_factory, n, seed, device):
+def _sample_surface(obj_factory, n, seed, device, return_faces=False):
     """n area-uniform fp64 surface points: stratified allocation of the samples to faces by cumulative area
     (face t receives round(cum_area_fraction(t) * n) - (samples so far), the Open3D rule behind sdf.py:654), then
     (1-sqrt(r1)) v0 + sqrt(r1)(1-r2) v1 + sqrt(r1) r2 v2 inside the face."""
@@ -822,7 +822,8 @@ def _sample_surface(obj_factory, n, seed, device):
     with torch.cuda.device(device):
         cum_dev = torch.from_numpy(upto).to(device)
         out = torch.empty(n, 3, dtype=torch.float64, device=device)
+        face = torch.empty(n, dtype=torch.int32, device=device) if return_faces else None
         nat.check(nat.lib().pvb_mesh_sample(nat.ptr(st["v64"]), nat.ptr(st["faces"]), len(areas), nat.ptr(cum_dev),
-                                            n, int(seed) & 0xFFFFFFFFFFFFFFFF, nat.ptr(out), None,
+                                            n, int(seed) & 0xFFFFFFFFFFFFFFFF, nat.ptr(out), nat.ptr(face),
                                             nat.stream_ptr(device)), "pvb_mesh_sample")
-    return out
+    return (out, face) if return_faces else out

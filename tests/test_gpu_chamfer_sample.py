@@ -89,16 +89,26 @@ def test_sample_mesh_points(name, tmp_path):
     assert not torch.equal(pts, pts4)
     with pytest.raises(RuntimeError):
         pv.sample_mesh_points(None, name="nope", num_points=7, dbpath=str(tmp_path / "none.pkl"))
-    # area uniformity: the share of samples per octant of the bounding box matches the share of surface area
+    # area uniformity: stratified allocation => every face holds round-to-nearest of (area share * n) samples
     from pytorch_volumetric_b200.sdf import _sample_surface
-    big = _sample_surface(obj, 400_000, 0, torch.device("cuda", 0)).cpu().numpy()
+    n_big = 400_000
+    big, face = _sample_surface(obj, n_big, 0, torch.device("cuda", 0), return_faces=True)
     vv, ff = workloads.fixture_mesh(name)
     tri = vv[ff]
     area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
-    cen = tri.mean(axis=1)
-    mid = 0.5 * (vv.min(0) + vv.max(0))
-    def octant(p):
-        return (p[:, 0] > mid[0]) * 4 + (p[:, 1] > mid[1]) * 2 + (p[:, 2] > mid[2]) * 1
-    share_area = np.bincount(octant(cen), weights=area, minlength=8) / area.sum()
-    share_pts = np.bincount(octant(big), minlength=8) / len(big)
-    assert np.abs(share_area - share_pts).max() < 0.02
+    counts = np.bincount(face.cpu().numpy(), minlength=len(ff))
+    assert counts.sum() == n_big and np.abs(counts - area / area.sum() * n_big).max() <= 1.0 + 1e-6
+    # every sample lies on its face: barycentric reconstruction
+    big = big.cpu().numpy()
+    t = tri[face.cpu().numpy()]
+    nrm = np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0])
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    assert np.abs(((big - t[:, 0]) * nrm).sum(-1)).max() < 1e-12
+    # and the samples are spread inside the faces: mean barycentric weights ~ 1/3 each
+    e0, e1, r = t[:, 1] - t[:, 0], t[:, 2] - t[:, 0], big - t[:, 0]
+    d00, d01, d11 = (e0 * e0).sum(-1), (e0 * e1).sum(-1), (e1 * e1).sum(-1)
+    d20, d21 = (r * e0).sum(-1), (r * e1).sum(-1)
+    den = d00 * d11 - d01 * d01
+    bv, bw = (d11 * d20 - d01 * d21) / den, (d00 * d21 - d01 * d20) / den
+    assert bv.min() > -1e-9 and bw.min() > -1e-9 and (bv + bw).max() < 1 + 1e-9
+    assert abs(bv.mean() - 1 / 3) < 5e-3 and abs(bw.mean() - 1 / 3) < 5e-3

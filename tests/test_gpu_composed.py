@@ -216,7 +216,9 @@ def test_robot_arm_batched_equals_looped(tmp_path):
         s.set_joint_configuration(th[i])
         v, g = s(pts)
         assert v.shape == (15251,)
-        assert torch.equal(v, all_val[i]) and torch.equal(g, all_grad[i])
+        # the reference's own tolerances (tests/test_model_to_sdf.py:211-212): FK of one configuration and of the
+        # batch may differ in the last bit of the transforms
+        assert torch.allclose(v, all_val[i]) and torch.allclose(g, all_grad[i], atol=1e-6)
     # independent recomposition: per-link CachedSDF calls on explicitly transformed points, argmin in torch
     s.set_joint_configuration(th)
     M = s.object_to_link_frames.get_matrix().reshape(8, 20, 4, 4)

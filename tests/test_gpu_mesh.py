@@ -39,7 +39,7 @@ def test_mesh_query_vs_oracle(name, n):
     ok = ~sign_bad
     bad_v, bad_g, rep = classify_mesh_mismatch(d_gpu[ok], g_gpu[ok], d_ref[ok], g_ref[ok], TOL, coord_scale=scale)
     assert bad_v == 0 and bad_g == 0, rep
-    assert rep["bad_grad"] <= 3e-3 * n, rep
+    assert rep["bad_grad"] <= 5e-3 * n, rep
     # closest point itself
     assert np.abs(res.closest.cpu().numpy() - c_ref.numpy()).max() < 1e-5 or rep["explained"] > 0
     # shapes / dtypes / device (sdf.py:166)
