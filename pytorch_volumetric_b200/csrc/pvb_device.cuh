@@ -281,70 +281,71 @@ __device__ __forceinline__ SdfOut mesh_eval(const pvb_sdf_desc &m, const NodeSta
 
 // ----------------------------------------------------------------------------
 // CachedSDF: nearest-voxel index (TorchMultidimView.ensure_index_key semantics).
-// Returns the ravelled key, or -1 when the point fails all(min <= p <= max).
-// The reference formula, exactly (TorchMultidimView.ensure_index_key): round((p - min) / res), in fp64 when the
-// range came from numpy (torch.tensor of numpy scalars is float64) and in fp32 for Python-float ranges.
-// Out of line: it runs for ~0.03 % of the coordinates and must not cost the streaming path registers.
-__device__ __noinline__ float grid_axis_index_exact(float pv, double min64, double res64, float min32, float res32,
-                                                    bool fp32_mode) {
-    if (fp32_mode) return rintf(__fdiv_rn(pv - min32, res32));
-    return (float)rint(__ddiv_rn((double)pv - min64, res64));
+//
+// The reference formula, exactly: round((p - min) / res), in fp64 when the range came from numpy (torch.tensor of
+// numpy scalars is float64) and in fp32 for Python-float ranges.  Out of line: it runs for ~0.03 % of the points
+// and must not cost the streaming path registers or instruction slots.
+__device__ __noinline__ int grid_axis_index_exact(float pv, double min64, double res64, float min32, float res32,
+                                                  bool fp32_mode, int n) {
+    float kf;
+    if (fp32_mode) kf = rintf(__fdiv_rn(pv - min32, res32));
+    else kf = (float)rint(__ddiv_rn((double)pv - min64, res64));
+    return min(max((int)kf, 0), n - 1);
 }
 
-__device__ __forceinline__ int grid_axis_index(const pvb_sdf_desc &g, int a, float pv) {
-    // fast path: fp32 estimate, accepted when it cannot round differently from the exact formula
-    const float q = (pv - g.min32[a]) * g.inv_res32[a];
-    float kf = rintf(q);
-    if (!(fabsf(q - kf) <= g.idx_certain[a]))   // inside the uncertainty band of a cell boundary
-        kf = grid_axis_index_exact(pv, g.min64[a], g.res64[a], g.min32[a], g.res32[a],
-                                   (g.flags & PVB_GRID_INDEX_FP32) != 0);
-    return min(max((int)kf, 0), g.dims[a] - 1);   // clamp: memory safety only
-}
-
-__device__ __forceinline__ long long grid_key(const pvb_sdf_desc &g, f3 p) {
-    const bool inb = (p.x >= g.valid_lo[0]) & (p.x <= g.valid_hi[0]) & (p.y >= g.valid_lo[1]) &
-                     (p.y <= g.valid_hi[1]) & (p.z >= g.valid_lo[2]) & (p.z <= g.valid_hi[2]);
-    if (!inb) return -1;
-    const int k0 = grid_axis_index(g, 0, p.x), k1 = grid_axis_index(g, 1, p.y), k2 = grid_axis_index(g, 2, p.z);
-    return (long long)((k0 * g.dims[1] + k1) * g.dims[2] + k2);   // < 2^31 voxels, checked by the ABI
-}
-
-// Point-to-AABB rule for out-of-range points (sdf.py:555-571).
-__device__ __forceinline__ SdfOut bbox_eval(const pvb_sdf_desc &g, f3 p) {
-    float dlt[3];
-    const float pv[3] = {p.x, p.y, p.z};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        float below = g.bb_min[a] - pv[a];
-        const bool on = below > 0.f;
-        below = on ? below : 0.f;
-        float above = pv[a] - g.bb_max[a];
-        above = above > 0.f ? above : 0.f;
-        const float t = below + above;
-        dlt[a] = on ? -t : t;
-    }
-    const float dist = sqrtf(dlt[0] * dlt[0] + dlt[1] * dlt[1] + dlt[2] * dlt[2]);
-    SdfOut o;
-    o.val = dist;
-    o.grad = mk3(__fdiv_rn(dlt[0], dist), __fdiv_rn(dlt[1], dist), __fdiv_rn(dlt[2], dist));
-    return o;
-}
-
-// kMesh = false compiles the tree walk out (BOUNDING_BOX-only instantiation: no stack, few registers).
+// The evaluator is written branch-free on purpose: the first version of this kernel spent 23 % of its issue slots
+// on BRA/BSSY/BSYNC and saturated the XU pipe (FRND/F2I/MUFU); see profiles/README.md.
+//   * rint / float->int by the 1.5*2^23 magic add (FADD on the FMA pipe, no XU op); valid for |q| < 2^22, and
+//     anything larger is out of range anyway
+//   * the fp32 estimate q = (p - min32) * inv_res32 is accepted when |q - rint(q)| <= idx_certain (it then provably
+//     rounds like the exact formula); otherwise ONE rare branch re-evaluates the three axes exactly
+//   * in-range gather is a predicated load; the point-to-AABB rule (sdf.py:555-571) is evaluated for every point
+//     with selects, its 1/dist by MUFU.RSQ + one Newton step (<= 1 ulp from the reference's sqrt + divide)
+// Returns the ravelled key through key_out (-1 when the point fails all(min <= p <= max)).
 template <bool kMesh>
 __device__ __forceinline__ SdfOut grid_eval(const pvb_sdf_desc &g, const NodeStage &st, f3 p, uint32_t mesh_mode,
                                             uint64_t idx, long long *key_out) {
-    const long long key = grid_key(g, p);
-    if (key_out) *key_out = key;
-    if (key >= 0) {
-        const float4 e = __ldg(reinterpret_cast<const float4 *>(g.table) + key);
-        SdfOut o; o.val = e.x; o.grad = mk3(e.y, e.z, e.w);
-        return o;
+    const float kMagic = 12582912.f;   // 1.5 * 2^23
+    const float qx = (p.x - g.min32[0]) * g.inv_res32[0];
+    const float qy = (p.y - g.min32[1]) * g.inv_res32[1];
+    const float qz = (p.z - g.min32[2]) * g.inv_res32[2];
+    const float mx = __fadd_rn(qx, kMagic), my = __fadd_rn(qy, kMagic), mz = __fadd_rn(qz, kMagic);
+    int kx = __float_as_int(mx) - 0x4B400000, ky = __float_as_int(my) - 0x4B400000,
+        kz = __float_as_int(mz) - 0x4B400000;
+    const bool certain = (fabsf(qx - __fsub_rn(mx, kMagic)) <= g.idx_certain[0]) &
+                         (fabsf(qy - __fsub_rn(my, kMagic)) <= g.idx_certain[1]) &
+                         (fabsf(qz - __fsub_rn(mz, kMagic)) <= g.idx_certain[2]);
+    const bool inb = (p.x >= g.valid_lo[0]) & (p.x <= g.valid_hi[0]) & (p.y >= g.valid_lo[1]) &
+                     (p.y <= g.valid_hi[1]) & (p.z >= g.valid_lo[2]) & (p.z <= g.valid_hi[2]);
+    if (inb & !certain) {   // rare: within the uncertainty band of a cell boundary
+        const bool f32 = (g.flags & PVB_GRID_INDEX_FP32) != 0;
+        kx = grid_axis_index_exact(p.x, g.min64[0], g.res64[0], g.min32[0], g.res32[0], f32, g.dims[0]);
+        ky = grid_axis_index_exact(p.y, g.min64[1], g.res64[1], g.min32[1], g.res32[1], f32, g.dims[1]);
+        kz = grid_axis_index_exact(p.z, g.min64[2], g.res64[2], g.min32[2], g.res32[2], f32, g.dims[2]);
     }
+    int key = (kx * g.dims[1] + ky) * g.dims[2] + kz;
+    key = max(min(key, g.dims[0] * g.dims[1] * g.dims[2] - 1), 0);   // memory safety only (exact when inb)
+    if (key_out) *key_out = inb ? (long long)key : -1ll;
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inb) e = __ldg(reinterpret_cast<const float4 *>(g.table) + key);
     if constexpr (kMesh) {
-        if (g.flags & PVB_GRID_OOB_GT) return mesh_eval(g, st, p, mesh_mode, idx, nullptr, nullptr);   // sdf.py:553-554
+        if (!inb && (g.flags & PVB_GRID_OOB_GT))
+            return mesh_eval(g, st, p, mesh_mode, idx, nullptr, nullptr);   // sdf.py:553-554
     }
-    return bbox_eval(g, p);
+    // point-to-AABB rule (sdf.py:555-571), branch-free
+    const float bx = g.bb_min[0] - p.x, by = g.bb_min[1] - p.y, bz = g.bb_min[2] - p.z;
+    const float ax = p.x - g.bb_max[0], ay = p.y - g.bb_max[1], az = p.z - g.bb_max[2];
+    const float tx = fmaxf(bx, 0.f) + fmaxf(ax, 0.f), ty = fmaxf(by, 0.f) + fmaxf(ay, 0.f),
+                tz = fmaxf(bz, 0.f) + fmaxf(az, 0.f);
+    const float dx = bx > 0.f ? -tx : tx, dy = by > 0.f ? -ty : ty, dz = bz > 0.f ? -tz : tz;
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    float r = rsqrtf(d2);                                   // MUFU.RSQ; +inf at d2 == 0
+    r = r * fmaf(-0.5f * d2 * r, r, 1.5f);                  // one Newton step: 1/sqrt(d2) to ~1 ulp
+    const float dist = d2 > 0.f ? d2 * r : 0.f;             // the reference yields 0 and NaN gradients here (0/0)
+    SdfOut o;
+    o.val = inb ? e.x : dist;
+    o.grad = mk3(inb ? e.y : dx * r, inb ? e.z : dy * r, inb ? e.w : dz * r);
+    return o;
 }
 
 __device__ __forceinline__ SdfOut sphere_eval(float radius, f3 p) {   // sdf.py:291-295
