@@ -55,50 +55,67 @@ def ncu_traffic(workload):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region through NVML (nvidia_ml_py) from a background
+    thread.  NVML is initialised before the warm-up so that no driver initialisation lands inside the timed region
+    (spawning `nvidia-smi -lms` there stalled kernel launches for milliseconds and tripled a 2 ms measurement)."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4), ("hw_power_brake", 0x80))
 
-    def __init__(self, index):
-        self.index = index
-        self.rows = []
-        self.proc = None
+    def __init__(self, index, period_s=0.002):
+        self.period = period_s
+        self.sm, self.reasons_seen, self.max = [], set(), None
+        self._run = False
+        self.h = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._sample()          # touch every entry point once, outside the timed region
+            self.sm.clear(); self.reasons_seen.clear()
+        except Exception as e:      # no NVML: report it, never fail the benchmark
+            self.err = repr(e)
+            self.h = None
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+            nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        for name, bit in self.REASONS:
+            if mask & bit:
+                self.reasons_seen.add(name)
+
+    def _loop(self):
+        while self._run:
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        if self.h is None:
+            return
+        self._run = True
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            c = [x.strip() for x in r.split(",")]
-            if len(c) < 6:
-                continue
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {getattr(self, 'err', '')}"]}
+        self._run = False
+        self.t.join(timeout=1)
+        if not self.sm:
             try:
-                sm.append(float(c[0])); mx.append(float(c[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, c[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self._sample()
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max,
+                "reasons": sorted(self.reasons_seen), "samples": len(self.sm)}
 
 
 def dist_setup(n_gpus):
@@ -141,7 +158,7 @@ class C2(Workload):
     """BASELINE C2: CachedSDF(res=0.005) on the drill, 10^7 uniform points over the cache range inflated 10 % per
     side (~42 % out of range -> AABB rule), 3 rotating input buffers (120 MB each, > L2)."""
     name = "c2"
-    kernel = "grid_lookup_vec4_kernel<false>"
+    kernel = "grid_lookup_tma_kernel"
     n_points = 10_000_000
 
     def __init__(self, rank, n_buffers=3, cache_dir=None):
@@ -441,8 +458,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -453,6 +470,7 @@ def main():
         return run_reference(args)
 
     rank, world, local = dist_setup(args.gpus)
+    sampler = ClockSampler(local)
     wl = make_workload(args.workload, rank, world)
     torch.cuda.synchronize()
 
@@ -462,7 +480,6 @@ def main():
     stream = torch.cuda.current_stream()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
     barrier(world)
     sampler.start()
     t_begin.record(stream)

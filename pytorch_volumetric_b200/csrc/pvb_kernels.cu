@@ -224,7 +224,10 @@ grid_lookup_vec4_kernel(const pvb_sdf_desc g, const float4 *__restrict__ pts4, l
 // (double buffered, mbarrier completion), threads read their 4 points with three conflict-free LDS.128, results
 // are staged in shared memory and leave with cp.async.bulk shared->global stores (bulk groups).  The LSU then
 // only executes the gathers.
-constexpr int kTmaThreads = 256;
+#ifndef PVB_TMA_THREADS
+#define PVB_TMA_THREADS 256
+#endif
+constexpr int kTmaThreads = PVB_TMA_THREADS;
 constexpr int kTmaTile = kTmaThreads * 4;              // points per tile
 struct __align__(128) GridTmaSmem {
     float in[2][kTmaTile * 3];                         // 2 x 12 KB
