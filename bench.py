@@ -55,13 +55,17 @@ def ncu_traffic(workload):
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region through NVML (nvidia_ml_py) from a background
-    thread.  NVML is initialised before the warm-up so that no driver initialisation lands inside the timed region
-    (spawning `nvidia-smi -lms` there stalled kernel launches for milliseconds and tripled a 2 ms measurement)."""
+    """SM clock + throttle reasons sampled DURING the timed region through NVML (nvidia_ml_py).
+
+    Measured on this pool (gpurun_out/bisect.log, round 1): NVML queries and `nvidia-smi -lms` contend with kernel
+    launches for a driver lock -- a 2 ms sampling period doubled the host issue time per step (25 -> 55 us) and
+    made a 58 us/step kernel loop host-bound.  So: NVML is initialised before the warm-up, a background thread
+    samples every 100 ms (long runs), and one sample is always taken right after the last timed launch has been
+    ENQUEUED, i.e. while the timed kernels are still executing on the GPU, where it cannot delay any launch."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
                ("sw_power_cap", 0x4), ("hw_power_brake", 0x80))
 
-    def __init__(self, index, period_s=0.002):
+    def __init__(self, index, period_s=0.1):
         self.period = period_s
         self.sm, self.reasons_seen, self.max = [], set(), None
         self._run = False
@@ -89,16 +93,25 @@ class ClockSampler:
             if mask & bit:
                 self.reasons_seen.add(name)
 
+    def sample_now(self):
+        if self.h is not None:
+            try:
+                self._sample()
+            except Exception:
+                pass
+
     def _loop(self):
         while self._run:
+            time.sleep(self.period)
+            if not self._run:
+                break
             try:
                 self._sample()
             except Exception:
                 break
-            time.sleep(self.period)
 
     def start(self):
-        if self.h is None:
+        if self.h is None or os.environ.get("PVB_BENCH_NO_SAMPLER"):
             return
         self._run = True
         self.t = threading.Thread(target=self._loop, daemon=True)
@@ -108,7 +121,8 @@ class ClockSampler:
         if self.h is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {getattr(self, 'err', '')}"]}
         self._run = False
-        self.t.join(timeout=1)
+        if hasattr(self, "t"):
+            self.t.join(timeout=1)
         if not self.sm:
             try:
                 self._sample()
@@ -478,21 +492,22 @@ def main():
     for i in range(args.warmup):
         wl.step(i)
     stream = torch.cuda.current_stream()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
     sampler.start()
+    t_cpu0 = time.perf_counter()
     t_begin.record(stream)
-    for i in range(args.steps):
-        ev[i][0].record(stream)
+    for i in range(args.steps):          # nothing but the public API call in the timed loop
         out = wl.step(i)
-        ev[i][1].record(stream)
     t_end.record(stream)
+    cpu_issue_us = (time.perf_counter() - t_cpu0) / args.steps * 1e6
+    sampler.sample_now()                 # the GPU is still executing the queued timed steps here
     barrier(world)
     clocks = sampler.stop()
     total_ms = max_over_ranks(t_begin.elapsed_time(t_end), world)
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    kernel_ms = statistics.mean(step_ms)
+    # device time per launch of the dominant kernel: the timed region is K back-to-back steps on one stream,
+    # bracketed by CUDA events on that stream
+    kernel_ms = t_begin.elapsed_time(t_end) / args.steps
     units_all = max_over_ranks(float(wl.units), world) * world if args.workload in ("c2", "mesh10k", "mesh50k") \
         else sum_over_ranks(float(wl.units), world)
     value = units_all * args.steps / (total_ms * 1e-3)
@@ -543,6 +558,7 @@ def main():
                 "scaling": "weak" if args.workload in ("c2", "mesh10k", "mesh50k") else "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.desc, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": wl.launches_per_step * args.steps, "roofline": roofline,
+                "host_issue_us_per_step": cpu_issue_us,
                 "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

@@ -59,8 +59,7 @@ enum {
 
 /*
  * One queryable object.  232 bytes (pvb_sizeof_sdf_desc()), POD, host-resident (device pointers
- * inside); arrays of these are copied to the device by the caller for the
- * composed kernels.
+ * inside); the composed kernels take a host array of these by value.
  *
  * GRID part  = CachedSDF state (sdf.py:521-525): interleaved table
  *              {val, gx, gy, gz} per voxel in C order (last axis fastest),
@@ -147,7 +146,7 @@ int pvb_grid_lookup(const pvb_sdf_desc *grid, const float *pts, int64_t n,
 int pvb_sphere_query(float radius, const float *pts, int64_t n, float *out_val, float *out_grad, void *stream);
 
 /* ---- ComposedSDF.__call__ / RobotSDF.__call__ (sdf.py:392-433, model_to_sdf.py:117-125) ----
- * descs_dev: DEVICE array of n_sdf pvb_sdf_desc; xforms: DEVICE float[n_sdf*n_cfg][16] object->sub-frame
+ * descs: HOST array of n_sdf (<= 128) pvb_sdf_desc, passed to the kernel by value (constant bank); xforms: DEVICE float[n_sdf*n_cfg][16] object->sub-frame
  * 4x4 row-major, sub-SDF-major (sdf.py:385-390).  The winning gradient is mapped back with
  * g_obj = g_link @ M[:3,:3]: the reference's link_frame_to_obj_frame[i].transform_normals
  * (sdf.py:380-383, 409) is g @ inv(inv(M)[:3,:3]), and the two inversions cancel;
@@ -155,7 +154,7 @@ int pvb_sphere_query(float radius, const float *pts, int64_t n, float *out_val, 
  * int32 argmin index.  cfg_begin/cfg_count select a contiguous slab of configurations (multi-GPU
  * sharding); outputs are indexed relative to cfg_begin.  needs_mesh != 0 when any descriptor is a MESH or a
  * GRID with PVB_GRID_OOB_GT (selects the instantiation that contains the tree walk). */
-int pvb_composed_query(const void *descs_dev, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
+int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
                        int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count,
                        const float *pts, int64_t n_pts, uint32_t mesh_mode,
                        float *out_val, float *out_grad, int32_t *out_which, void *stream);

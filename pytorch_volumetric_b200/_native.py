@@ -93,7 +93,7 @@ _SIGNATURES = {
                                        ctypes.c_void_p]),
     "pvb_sphere_query": (ctypes.c_int, [ctypes.c_float, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p]),
-    "pvb_composed_query": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+    "pvb_composed_query": (ctypes.c_int, [ctypes.POINTER(SdfDesc), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -206,11 +206,9 @@ def bvh_build(verts32, faces32):
     return nodes[:n_nodes.value].copy(), tris, int(depth.value)
 
 
-def descs_to_device(descs, device):
-    """Pack a list of SdfDesc into one device byte tensor for the composed kernels."""
-    n = len(descs)
-    size = ctypes.sizeof(SdfDesc)
-    buf = np.empty(n * size, dtype=np.uint8)
+def desc_array(descs):
+    """Contiguous host array of pvb_sdf_desc for the composed kernels (passed to the kernel by value)."""
+    arr = (SdfDesc * len(descs))()
     for i, d in enumerate(descs):
-        buf[i * size:(i + 1) * size] = np.frombuffer(bytes(d), dtype=np.uint8)
-    return torch.from_numpy(buf).to(device)
+        ctypes.memmove(ctypes.byref(arr[i]), ctypes.byref(d), ctypes.sizeof(SdfDesc))
+    return arr

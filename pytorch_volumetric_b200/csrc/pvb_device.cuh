@@ -302,7 +302,10 @@ __device__ __noinline__ int grid_axis_index_exact(float pv, double min64, double
 //   * in-range gather is a predicated load; the point-to-AABB rule (sdf.py:555-571) is evaluated for every point
 //     with selects, its 1/dist by MUFU.RSQ + one Newton step (<= 1 ulp from the reference's sqrt + divide)
 // Returns the ravelled key through key_out (-1 when the point fails all(min <= p <= max)).
-template <bool kMesh>
+// kBranchOOB: skip the AABB rule with a branch when the point is in range (composed kernels, where out-of-range
+// points are rare and warps mostly agree) instead of evaluating it for every point with selects (streaming kernel,
+// 42 % out of range at C2: both sides would run anyway).
+template <bool kMesh, bool kBranchOOB = false>
 __device__ __forceinline__ SdfOut grid_eval(const pvb_sdf_desc &g, const NodeStage &st, f3 p, uint32_t mesh_mode,
                                             uint64_t idx, long long *key_out) {
     const float kMagic = 12582912.f;   // 1.5 * 2^23
@@ -331,6 +334,12 @@ __device__ __forceinline__ SdfOut grid_eval(const pvb_sdf_desc &g, const NodeSta
     if constexpr (kMesh) {
         if (!inb && (g.flags & PVB_GRID_OOB_GT))
             return mesh_eval(g, st, p, mesh_mode, idx, nullptr, nullptr);   // sdf.py:553-554
+    }
+    if constexpr (kBranchOOB) {
+        if (inb) {
+            SdfOut o; o.val = e.x; o.grad = mk3(e.y, e.z, e.w);
+            return o;
+        }
     }
     // point-to-AABB rule (sdf.py:555-571), branch-free
     const float bx = g.bb_min[0] - p.x, by = g.bb_min[1] - p.y, bz = g.bb_min[2] - p.z;

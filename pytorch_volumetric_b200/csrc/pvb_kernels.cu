@@ -330,30 +330,42 @@ __global__ void sphere_kernel(float radius, const float *__restrict__ pts, long 
 }
 
 // ============================================================ composed query
-// One thread per (configuration, point): walks the S sub-SDFs in registers --
-// transform into the sub-frame, evaluate, keep the running min (first index on
-// ties, as torch.argmin), rotate the winning gradient back -- and writes
-// (val, grad) once.  The S*|A|*P*3 intermediates of sdf.py:399-415 never exist.
+// One thread per (configuration, 1 or 4 points): walks the S sub-SDFs in registers -- transform into the sub-frame,
+// evaluate, keep the running min (first index on ties, as torch.argmin), rotate the winning gradient back -- and
+// writes (val, grad) once.  The S*|A|*P*3 intermediates of sdf.py:399-415 never exist.
+//
+// Where the time goes is the LSU: a random 16-byte table gather costs ~2 L1 wavefront-cycles per lane (measured,
+// scripts/ubench_gather.cu), and so does every warp-uniform LDS/LDG.  Hence
+//   * the descriptors travel as a __grid_constant__ kernel parameter (constant bank, uniform datapath, no LSU);
+//     the first version staged them in shared memory and spent more LSU cycles on descriptor fields than on gathers
+//   * 4 points per thread: one broadcast read of a link transform serves 4 points; points / results move as
+//     128-bit coalesced loads and stores
+//   * exact pruning: a sub-SDF whose AABB lower bound already exceeds the running min cannot be the argmin
+//     (margin measured on the table at build time), compared on squared distances (no MUFU)
 constexpr int kCompThreads = 256;
-constexpr int kCompMaxSmemSdf = 32;
+constexpr int kCompSmemXf = 64;
+#ifndef PVB_COMP_PTS
+#define PVB_COMP_PTS 4        // points per thread on the vector path (1, 2 or 4)
+#endif
+#ifndef PVB_COMP_MINB
+#define PVB_COMP_MINB 2
+#endif
 
-template <bool kMesh>
-__global__ void __launch_bounds__(kCompThreads)
-composed_query_kernel(const pvb_sdf_desc *__restrict__ descs, int n_sdf, const float *__restrict__ xforms,
-                      int n_cfg, int cfg_begin, int cfg_count,
-                      const float *__restrict__ pts, long long n_pts, uint32_t mesh_mode,
-                      float *__restrict__ out_val, float *__restrict__ out_grad, int *__restrict__ out_which) {
-    __shared__ pvb_sdf_desc s_desc[kCompMaxSmemSdf];
-    __shared__ float s_xf[kCompMaxSmemSdf][12];
-    const bool use_smem = n_sdf <= kCompMaxSmemSdf;
+template <int MAXS>
+struct DescPack {
+    pvb_sdf_desc d[MAXS];
+};
+
+template <bool kMesh, int PTS, int MAXS>
+__global__ void __launch_bounds__(kCompThreads, (PTS > 1 ? PVB_COMP_MINB : 1))
+composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, const float *__restrict__ xforms,
+                      int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, long long first_pt,
+                      long long n_pts, uint32_t mesh_mode, float *__restrict__ out_val, float *__restrict__ out_grad,
+                      int *__restrict__ out_which) {
+    __shared__ float s_xf[kCompSmemXf][12];
+    const bool use_smem = n_sdf <= kCompSmemXf;
     NodeStage st; st.smem = nullptr; st.n = 0;
-    if (use_smem) {
-        // descriptors are configuration independent: stage them once per block
-        const int words = n_sdf * (int)(sizeof(pvb_sdf_desc) / 4);
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(descs);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(s_desc);
-        for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
-    }
+    const long long n_items = (n_pts - first_pt) / PTS;     // work items of PTS consecutive points
     for (int c = blockIdx.y; c < cfg_count; c += gridDim.y) {
         const int cfg = cfg_begin + c;
         __syncthreads();
@@ -365,43 +377,100 @@ composed_query_kernel(const pvb_sdf_desc *__restrict__ descs, int n_sdf, const f
         }
         __syncthreads();
         const long long stride = (long long)gridDim.x * blockDim.x;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
-            const f3 p = load_point(pts, i);
-            float best = PVB_INF;
-            f3 bg = mk3(0.f, 0.f, 0.f);
-            int bs = -1;
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_items; t += stride) {
+            const long long i0 = first_pt + t * PTS;
+            f3 p[PTS];
+            if constexpr (PTS == 4) {
+                const float4 *src = reinterpret_cast<const float4 *>(pts + 3 * i0);
+                const float4 a = __ldg(src), b = __ldg(src + 1), cc = __ldg(src + 2);
+                p[0] = mk3(a.x, a.y, a.z); p[1] = mk3(a.w, b.x, b.y); p[2] = mk3(b.z, b.w, cc.x);
+                p[3] = mk3(cc.y, cc.z, cc.w);
+            } else if constexpr (PTS == 2) {
+                const float2 *src = reinterpret_cast<const float2 *>(pts + 3 * i0);
+                const float2 a = __ldg(src), b = __ldg(src + 1), cc = __ldg(src + 2);
+                p[0] = mk3(a.x, a.y, b.x); p[1] = mk3(b.y, cc.x, cc.y);
+            } else {
+                p[0] = load_point(pts, i0);
+            }
+            float best[PTS];
+            f3 bg[PTS];
+            int bs[PTS];
+#pragma unroll
+            for (int k = 0; k < PTS; ++k) { best[k] = PVB_INF; bg[k] = mk3(0.f, 0.f, 0.f); bs[k] = -1; }
             for (int s = 0; s < n_sdf; ++s) {
-                const pvb_sdf_desc &d = use_smem ? s_desc[s] : descs[s];
-                const float *xf = use_smem ? s_xf[s] : xforms + ((size_t)s * n_cfg + cfg) * 16;
-                // Transform3d.transform_points: R p + t  (sdf.py:399)
-                const f3 q = mk3(fmaf(xf[0], p.x, fmaf(xf[1], p.y, fmaf(xf[2], p.z, xf[3]))),
-                                 fmaf(xf[4], p.x, fmaf(xf[5], p.y, fmaf(xf[6], p.z, xf[7]))),
-                                 fmaf(xf[8], p.x, fmaf(xf[9], p.y, fmaf(xf[10], p.z, xf[11]))));
-                // exact pruning: a sub-SDF whose value is provably > best cannot be the argmin
-                if (bs >= 0) {
-                    if (d.kind == PVB_KIND_GRID && (d.flags & PVB_GRID_PRUNE_OK)) {
-                        if (aabb_lower_bound(d, q) - d.prune_margin > best) continue;
-                    }
+                const pvb_sdf_desc &d = descs.d[s];
+                float xf[12];
+                if (use_smem) {
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) xf[e] = s_xf[s][e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) xf[e] = __ldg(xforms + ((size_t)s * n_cfg + cfg) * 16 + e);
                 }
-                SdfOut o;
-                const uint64_t idx = ((uint64_t)c * (uint64_t)n_pts + (uint64_t)i) * (uint64_t)n_sdf + (uint64_t)s;
-                if (d.kind == PVB_KIND_GRID) o = grid_eval<kMesh>(d, st, q, mesh_mode, idx, nullptr);
-                else if (kMesh && d.kind == PVB_KIND_MESH) o = mesh_eval(d, st, q, mesh_mode, idx, nullptr, nullptr);
-                else o = sphere_eval(d.radius, q);
-                if (o.val < best || bs < 0) {   // strict <: first index wins ties (torch.argmin, sdf.py:421)
-                    best = o.val; bg = o.grad; bs = s;
+                const bool prunable = d.kind == PVB_KIND_GRID && (d.flags & PVB_GRID_PRUNE_OK);
+#pragma unroll
+                for (int k = 0; k < PTS; ++k) {
+                    // Transform3d.transform_points: R p + t  (sdf.py:399)
+                    const f3 q = mk3(fmaf(xf[0], p[k].x, fmaf(xf[1], p[k].y, fmaf(xf[2], p[k].z, xf[3]))),
+                                     fmaf(xf[4], p[k].x, fmaf(xf[5], p[k].y, fmaf(xf[6], p[k].z, xf[7]))),
+                                     fmaf(xf[8], p[k].x, fmaf(xf[9], p[k].y, fmaf(xf[10], p[k].z, xf[11]))));
+                    if (prunable && bs[k] >= 0) {
+                        // value >= dist(q, AABB) - margin: skip when that bound already exceeds the running min
+                        const float thr = best[k] + d.prune_margin;
+                        const float ex = fmaxf(fmaxf(d.bb_min[0] - q.x, q.x - d.bb_max[0]), 0.f);
+                        const float ey = fmaxf(fmaxf(d.bb_min[1] - q.y, q.y - d.bb_max[1]), 0.f);
+                        const float ez = fmaxf(fmaxf(d.bb_min[2] - q.z, q.z - d.bb_max[2]), 0.f);
+                        const float lb2 = ex * ex + ey * ey + ez * ez;
+                        if (thr < 0.f || lb2 > thr * thr) continue;
+                    }
+                    SdfOut o;
+                    const uint64_t idx = ((uint64_t)c * (uint64_t)n_pts + (uint64_t)(i0 + k)) * (uint64_t)n_sdf + (uint64_t)s;
+                    if (d.kind == PVB_KIND_GRID) o = grid_eval<kMesh, true>(d, st, q, mesh_mode, idx, nullptr);
+                    else if (kMesh && d.kind == PVB_KIND_MESH) o = mesh_eval(d, st, q, mesh_mode, idx, nullptr, nullptr);
+                    else o = sphere_eval(d.radius, q);
+                    if (o.val < best[k] || bs[k] < 0) {   // strict <: first index wins ties (torch.argmin, sdf.py:421)
+                        best[k] = o.val; bg[k] = o.grad; bs[k] = s;
+                    }
                 }
             }
             // link_frame_to_obj_frame[i].transform_normals(g) = g @ inv(inv(M)[:3,:3]) = g @ M[:3,:3]
             // (sdf.py:380-383, 409): the double inversion cancels, no inverse is needed.
-            const float *G = use_smem ? s_xf[max(bs, 0)] : xforms + ((size_t)max(bs, 0) * n_cfg + cfg) * 16;
-            const f3 go = mk3(fmaf(bg.x, G[0], fmaf(bg.y, G[4], bg.z * G[8])),
-                              fmaf(bg.x, G[1], fmaf(bg.y, G[5], bg.z * G[9])),
-                              fmaf(bg.x, G[2], fmaf(bg.y, G[6], bg.z * G[10])));
-            const long long o_i = (long long)c * n_pts + i;
-            out_val[o_i] = best;
-            out_grad[3 * o_i] = go.x; out_grad[3 * o_i + 1] = go.y; out_grad[3 * o_i + 2] = go.z;
-            if (out_which) out_which[o_i] = bs;
+            f3 go[PTS];
+#pragma unroll
+            for (int k = 0; k < PTS; ++k) {
+                const int sb = max(bs[k], 0);
+                float G[12];
+                if (use_smem) {
+#pragma unroll
+                    for (int e = 0; e < 11; ++e) G[e] = s_xf[sb][e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 11; ++e) G[e] = __ldg(xforms + ((size_t)sb * n_cfg + cfg) * 16 + e);
+                }
+                go[k] = mk3(fmaf(bg[k].x, G[0], fmaf(bg[k].y, G[4], bg[k].z * G[8])),
+                            fmaf(bg[k].x, G[1], fmaf(bg[k].y, G[5], bg[k].z * G[9])),
+                            fmaf(bg[k].x, G[2], fmaf(bg[k].y, G[6], bg[k].z * G[10])));
+            }
+            const long long o_i = (long long)c * n_pts + i0;
+            if constexpr (PTS == 4) {
+                __stcs(reinterpret_cast<float4 *>(out_val + o_i), make_float4(best[0], best[1], best[2], best[3]));
+                float4 *dg = reinterpret_cast<float4 *>(out_grad + 3 * o_i);
+                __stcs(dg, make_float4(go[0].x, go[0].y, go[0].z, go[1].x));
+                __stcs(dg + 1, make_float4(go[1].y, go[1].z, go[2].x, go[2].y));
+                __stcs(dg + 2, make_float4(go[2].z, go[3].x, go[3].y, go[3].z));
+                if (out_which) *reinterpret_cast<int4 *>(out_which + o_i) = make_int4(bs[0], bs[1], bs[2], bs[3]);
+            } else if constexpr (PTS == 2) {
+                __stcs(reinterpret_cast<float2 *>(out_val + o_i), make_float2(best[0], best[1]));
+                float2 *dg = reinterpret_cast<float2 *>(out_grad + 3 * o_i);
+                __stcs(dg, make_float2(go[0].x, go[0].y));
+                __stcs(dg + 1, make_float2(go[0].z, go[1].x));
+                __stcs(dg + 2, make_float2(go[1].y, go[1].z));
+                if (out_which) *reinterpret_cast<int2 *>(out_which + o_i) = make_int2(bs[0], bs[1]);
+            } else {
+                out_val[o_i] = best[0];
+                out_grad[3 * o_i] = go[0].x; out_grad[3 * o_i + 1] = go[0].y; out_grad[3 * o_i + 2] = go[0].z;
+                if (out_which) out_which[o_i] = bs[0];
+            }
         }
     }
 }
@@ -665,29 +734,61 @@ extern "C" int pvb_sphere_query(float radius, const float *pts, int64_t n, float
     return PVB_OK;
 }
 
-extern "C" int pvb_composed_query(const void *descs_dev, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
+template <bool kMesh, int PTS, int MAXS>
+static int launch_composed(const pvb_sdf_desc *descs, int n_sdf, const float *xforms, int n_cfg, int cfg_begin,
+                           int cfg_count, const float *pts, long long first_pt, long long n_pts, uint32_t mesh_mode,
+                           float *out_val, float *out_grad, int *out_which, cudaStream_t stream) {
+    const long long n_items = (n_pts - first_pt) / PTS;
+    if (n_items <= 0) return PVB_OK;
+    DescPack<MAXS> pack;
+    memcpy(pack.d, descs, sizeof(pvb_sdf_desc) * (size_t)n_sdf);
+    const int gx = grid_for(n_items, kCompThreads, 8);
+    int gy = cfg_count < 65535 ? cfg_count : 65535;
+    const long long cap = (long long)sm_count() * 64;     // bound the block count for huge configuration batches
+    if ((long long)gx * gy > cap) { gy = (int)(cap / gx); if (gy < 1) gy = 1; }
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    composed_query_kernel<kMesh, PTS, MAXS><<<grid, kCompThreads, 0, stream>>>(
+        pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, first_pt, n_pts, mesh_mode, out_val, out_grad, out_which);
+    PVB_CHECK_LAUNCH("pvb_composed_query");
+    return PVB_OK;
+}
+
+extern "C" int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
                                   int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count,
-                                  const float *pts, int64_t n_pts, uint32_t mesh_mode, float *out_val, float *out_grad, int32_t *out_which,
-                                  void *stream) {
-    if (!descs_dev || !xforms || n_sdf < 1 || n_cfg < 1 || cfg_begin < 0 || cfg_count < 0 ||
+                                  const float *pts, int64_t n_pts, uint32_t mesh_mode, float *out_val, float *out_grad,
+                                  int32_t *out_which, void *stream) {
+    if (!descs || !xforms || n_sdf < 1 || n_cfg < 1 || cfg_begin < 0 || cfg_count < 0 ||
         cfg_begin + cfg_count > n_cfg || n_pts < 0 || (n_pts > 0 && cfg_count > 0 && (!pts || !out_val || !out_grad))) {
         pvb_set_error("pvb_composed_query: invalid argument (n_sdf=%d n_cfg=%d cfg=[%d,+%d) n_pts=%lld)", n_sdf, n_cfg,
                       cfg_begin, cfg_count, (long long)n_pts);
         return PVB_ERR_INVALID;
     }
+    if (n_sdf > 128) {
+        pvb_set_error("pvb_composed_query: at most 128 sub-SDFs per call (got %d)", n_sdf);
+        return PVB_ERR_INVALID;
+    }
     if (n_pts == 0 || cfg_count == 0) return PVB_OK;
-    const int gx = grid_for(n_pts, kCompThreads, 8);
-    int gy = cfg_count < 65535 ? cfg_count : 65535;
-    // keep the total block count bounded for huge config batches
-    const long long cap = (long long)sm_count() * 64;
-    if ((long long)gx * gy > cap) { gy = (int)(cap / gx); if (gy < 1) gy = 1; }
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    auto kern = needs_mesh ? composed_query_kernel<true> : composed_query_kernel<false>;
-    kern<<<grid, kCompThreads, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const pvb_sdf_desc *>(descs_dev), n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts,
-        n_pts, mesh_mode, out_val, out_grad, out_which);
-    PVB_CHECK_LAUNCH("pvb_composed_query");
-    return PVB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    auto aligned16 = [](const void *p) { return p == nullptr || ((uintptr_t)p % 16) == 0; };
+    // 4-points-per-thread vector path needs 16-byte aligned rows: every configuration slab starts at c * n_pts
+    const bool vec = !needs_mesh && aligned16(pts) && aligned16(out_val) && aligned16(out_grad) &&
+                     aligned16(out_which) && (n_pts % 4 == 0);
+    const long long n_vec = vec ? n_pts : 0;
+    int rc = PVB_OK;
+#define PVB_COMP(MESH, PTS, FIRST, N)                                                                              \
+    (n_sdf <= 16 ? launch_composed<MESH, PTS, 16>(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, FIRST, N,  \
+                                                  mesh_mode, out_val, out_grad, out_which, s)                      \
+                 : launch_composed<MESH, PTS, 128>(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, FIRST, N, \
+                                                   mesh_mode, out_val, out_grad, out_which, s))
+    if (n_vec > 0) {
+        rc = PVB_COMP(false, PVB_COMP_PTS, 0, n_pts);
+    } else if (needs_mesh) {
+        rc = PVB_COMP(true, 1, 0, n_pts);
+    } else {
+        rc = PVB_COMP(false, 1, 0, n_pts);
+    }
+#undef PVB_COMP
+    return rc;
 }
 
 extern "C" int64_t pvb_chamfer_workspace(int64_t n_pts) {

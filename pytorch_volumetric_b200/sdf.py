@@ -456,7 +456,9 @@ class ComposedSDF(ObjectFrameSDF):
                 hit = (None, False, None)
             else:
                 needs_mesh = any(d.kind == nat.PVB_KIND_MESH or (d.flags & nat.PVB_GRID_OOB_GT) for d in descs)
-                hit = (nat.descs_to_device(descs, device), needs_mesh, descs)
+                if len(descs) > 128:
+                    raise ValueError("ComposedSDF: at most 128 sub-SDFs are supported by the fused kernel")
+                hit = (nat.desc_array(descs), needs_mesh, descs)
             self._desc_cache = {key: hit}
         return hit[0], hit[1]
 
@@ -478,14 +480,14 @@ class ComposedSDF(ObjectFrameSDF):
         with torch.cuda.device(device):
             p = nat.as_f32_points(points_in_object_frame, device)
             P = p.shape[0]
-            descs_dev, needs_mesh = self._native_descs(device)
-            if descs_dev is None:
+            descs_arr, needs_mesh = self._native_descs(device)
+            if descs_arr is None:
                 return self._generic_query(p, cfg_begin, cfg_count, n_cfg, return_which)
             xf = self._xforms_on(device)
             val = torch.empty(cfg_count * P, dtype=torch.float32, device=device)
             grad = torch.empty(cfg_count * P, 3, dtype=torch.float32, device=device)
             which = torch.empty(cfg_count * P, dtype=torch.int32, device=device) if return_which else None
-            nat.check(nat.lib().pvb_composed_query(nat.ptr(descs_dev), S, int(needs_mesh), nat.ptr(xf), n_cfg,
+            nat.check(nat.lib().pvb_composed_query(descs_arr, S, int(needs_mesh), nat.ptr(xf), n_cfg,
                                                    cfg_begin, cfg_count, nat.ptr(p), P, nat.PVB_MESH_DEFAULT,
                                                    nat.ptr(val), nat.ptr(grad), nat.ptr(which),
                                                    nat.stream_ptr(device)), "pvb_composed_query")
