@@ -345,10 +345,16 @@ __global__ void sphere_kernel(float radius, const float *__restrict__ pts, long 
 constexpr int kCompThreads = 256;
 constexpr int kCompSmemXf = 64;
 #ifndef PVB_COMP_PTS
-#define PVB_COMP_PTS 4        // points per thread on the vector path (1, 2 or 4)
+#define PVB_COMP_PTS 2        // points per thread on the vector path (1, 2 or 4)
 #endif
 #ifndef PVB_COMP_MINB
-#define PVB_COMP_MINB 2
+#define PVB_COMP_MINB 4
+#endif
+#ifndef PVB_COMP_BESTFIRST
+// 1: evaluate the sub-SDF with the smallest AABB lower bound first (an extra pass over the transforms).  Measured
+// on C4 (profiles/README.md): fewer table gathers but 1.8x slower -- the kernel is instruction-issue bound, the
+// extra pass costs more than the gathers it saves.  Kept for reference.
+#define PVB_COMP_BESTFIRST 0
 #endif
 
 template <int MAXS>
@@ -362,7 +368,7 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
                       int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, long long first_pt,
                       long long n_pts, uint32_t mesh_mode, float *__restrict__ out_val, float *__restrict__ out_grad,
                       int *__restrict__ out_which) {
-    __shared__ float s_xf[kCompSmemXf][12];
+    __shared__ __align__(16) float s_xf[kCompSmemXf][12];
     const bool use_smem = n_sdf <= kCompSmemXf;
     NodeStage st; st.smem = nullptr; st.n = 0;
     const long long n_items = (n_pts - first_pt) / PTS;     // work items of PTS consecutive points
@@ -397,40 +403,89 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
             int bs[PTS];
 #pragma unroll
             for (int k = 0; k < PTS; ++k) { best[k] = PVB_INF; bg[k] = mk3(0.f, 0.f, 0.f); bs[k] = -1; }
+
+            auto load_xf = [&](int s, float4 &r0, float4 &r1, float4 &r2) {
+                if (use_smem) {
+                    const float4 *row = reinterpret_cast<const float4 *>(s_xf[s]);      // 3 x LDS.128 broadcast
+                    r0 = row[0]; r1 = row[1]; r2 = row[2];
+                } else {
+                    const float4 *row = reinterpret_cast<const float4 *>(xforms + ((size_t)s * n_cfg + cfg) * 16);
+                    r0 = __ldg(row); r1 = __ldg(row + 1); r2 = __ldg(row + 2);
+                }
+            };
+            auto xform = [](const float4 &r0, const float4 &r1, const float4 &r2, f3 v) {
+                // Transform3d.transform_points: R p + t  (sdf.py:399)
+                return mk3(fmaf(r0.x, v.x, fmaf(r0.y, v.y, fmaf(r0.z, v.z, r0.w))),
+                           fmaf(r1.x, v.x, fmaf(r1.y, v.y, fmaf(r1.z, v.z, r1.w))),
+                           fmaf(r2.x, v.x, fmaf(r2.y, v.y, fmaf(r2.z, v.z, r2.w))));
+            };
+            auto aabb_lb2 = [](const pvb_sdf_desc &d, f3 q) {
+                const float ex = fmaxf(fmaxf(d.bb_min[0] - q.x, q.x - d.bb_max[0]), 0.f);
+                const float ey = fmaxf(fmaxf(d.bb_min[1] - q.y, q.y - d.bb_max[1]), 0.f);
+                const float ez = fmaxf(fmaxf(d.bb_min[2] - q.z, q.z - d.bb_max[2]), 0.f);
+                return ex * ex + ey * ey + ez * ez;
+            };
+            auto evaluate = [&](const pvb_sdf_desc &d, int s, int k, f3 q) {
+                SdfOut o;
+                const uint64_t idx = ((uint64_t)c * (uint64_t)n_pts + (uint64_t)(i0 + k)) * (uint64_t)n_sdf + (uint64_t)s;
+                if (d.kind == PVB_KIND_GRID) o = grid_eval<kMesh, true>(d, st, q, mesh_mode, idx, nullptr);
+                else if (kMesh && d.kind == PVB_KIND_MESH) o = mesh_eval(d, st, q, mesh_mode, idx, nullptr, nullptr);
+                else o = sphere_eval(d.radius, q);
+                // torch.argmin semantics (sdf.py:421): smallest value, first index on ties -- whatever the visiting order
+                if (bs[k] < 0 || o.val < best[k] || (o.val == best[k] && s < bs[k])) {
+                    best[k] = o.val; bg[k] = o.grad; bs[k] = s;
+                }
+            };
+
+            // pass 1 (no table access): the sub-SDF with the smallest AABB lower bound is evaluated first so that
+            // the running min is tight before anything else is considered
+            int first[PTS];
+            if (PVB_COMP_BESTFIRST && n_sdf > 1) {
+                float lbmin[PTS];
+#pragma unroll
+                for (int k = 0; k < PTS; ++k) { lbmin[k] = PVB_INF; first[k] = 0; }
+                for (int s = 0; s < n_sdf; ++s) {
+                    float4 r0, r1, r2;
+                    load_xf(s, r0, r1, r2);
+#pragma unroll
+                    for (int k = 0; k < PTS; ++k) {
+                        const float lb2 = aabb_lb2(descs.d[s], xform(r0, r1, r2, p[k]));
+                        if (lb2 < lbmin[k]) { lbmin[k] = lb2; first[k] = s; }
+                    }
+                }
+                // evaluate each point's first choice; the loop keeps the descriptor index warp-uniform
+                // (constant-bank reads with a per-lane index would be replayed per distinct value)
+                for (int s = 0; s < n_sdf; ++s) {
+                    bool any = false;
+#pragma unroll
+                    for (int k = 0; k < PTS; ++k) any |= (first[k] == s);
+                    if (!any) continue;
+                    float4 r0, r1, r2;
+                    load_xf(s, r0, r1, r2);
+#pragma unroll
+                    for (int k = 0; k < PTS; ++k)
+                        if (first[k] == s) evaluate(descs.d[s], s, k, xform(r0, r1, r2, p[k]));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < PTS; ++k) first[k] = -1;
+            }
+            // pass 2: everything else, skipped when provably not the argmin
             for (int s = 0; s < n_sdf; ++s) {
                 const pvb_sdf_desc &d = descs.d[s];
-                float xf[12];
-                if (use_smem) {
-#pragma unroll
-                    for (int e = 0; e < 12; ++e) xf[e] = s_xf[s][e];
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 12; ++e) xf[e] = __ldg(xforms + ((size_t)s * n_cfg + cfg) * 16 + e);
-                }
+                float4 r0, r1, r2;
+                load_xf(s, r0, r1, r2);
                 const bool prunable = d.kind == PVB_KIND_GRID && (d.flags & PVB_GRID_PRUNE_OK);
 #pragma unroll
                 for (int k = 0; k < PTS; ++k) {
-                    // Transform3d.transform_points: R p + t  (sdf.py:399)
-                    const f3 q = mk3(fmaf(xf[0], p[k].x, fmaf(xf[1], p[k].y, fmaf(xf[2], p[k].z, xf[3]))),
-                                     fmaf(xf[4], p[k].x, fmaf(xf[5], p[k].y, fmaf(xf[6], p[k].z, xf[7]))),
-                                     fmaf(xf[8], p[k].x, fmaf(xf[9], p[k].y, fmaf(xf[10], p[k].z, xf[11]))));
+                    if (s == first[k]) continue;
+                    const f3 q = xform(r0, r1, r2, p[k]);
                     if (prunable && bs[k] >= 0) {
                         // value >= dist(q, AABB) - margin: skip when that bound already exceeds the running min
                         const float thr = best[k] + d.prune_margin;
-                        const float ex = fmaxf(fmaxf(d.bb_min[0] - q.x, q.x - d.bb_max[0]), 0.f);
-                        const float ey = fmaxf(fmaxf(d.bb_min[1] - q.y, q.y - d.bb_max[1]), 0.f);
-                        const float ez = fmaxf(fmaxf(d.bb_min[2] - q.z, q.z - d.bb_max[2]), 0.f);
-                        const float lb2 = ex * ex + ey * ey + ez * ez;
-                        if (thr < 0.f || lb2 > thr * thr) continue;
+                        if (thr < 0.f || aabb_lb2(d, q) > thr * thr) continue;
                     }
-                    SdfOut o;
-                    const uint64_t idx = ((uint64_t)c * (uint64_t)n_pts + (uint64_t)(i0 + k)) * (uint64_t)n_sdf + (uint64_t)s;
-                    if (d.kind == PVB_KIND_GRID) o = grid_eval<kMesh, true>(d, st, q, mesh_mode, idx, nullptr);
-                    else if (kMesh && d.kind == PVB_KIND_MESH) o = mesh_eval(d, st, q, mesh_mode, idx, nullptr, nullptr);
-                    else o = sphere_eval(d.radius, q);
-                    if (o.val < best[k] || bs[k] < 0) {   // strict <: first index wins ties (torch.argmin, sdf.py:421)
-                        best[k] = o.val; bg[k] = o.grad; bs[k] = s;
-                    }
+                    evaluate(d, s, k, q);
                 }
             }
             // link_frame_to_obj_frame[i].transform_normals(g) = g @ inv(inv(M)[:3,:3]) = g @ M[:3,:3]
@@ -439,17 +494,11 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
 #pragma unroll
             for (int k = 0; k < PTS; ++k) {
                 const int sb = max(bs[k], 0);
-                float G[12];
-                if (use_smem) {
-#pragma unroll
-                    for (int e = 0; e < 11; ++e) G[e] = s_xf[sb][e];
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 11; ++e) G[e] = __ldg(xforms + ((size_t)sb * n_cfg + cfg) * 16 + e);
-                }
-                go[k] = mk3(fmaf(bg[k].x, G[0], fmaf(bg[k].y, G[4], bg[k].z * G[8])),
-                            fmaf(bg[k].x, G[1], fmaf(bg[k].y, G[5], bg[k].z * G[9])),
-                            fmaf(bg[k].x, G[2], fmaf(bg[k].y, G[6], bg[k].z * G[10])));
+                float4 r0, r1, r2;
+                load_xf(sb, r0, r1, r2);
+                go[k] = mk3(fmaf(bg[k].x, r0.x, fmaf(bg[k].y, r1.x, bg[k].z * r2.x)),
+                            fmaf(bg[k].x, r0.y, fmaf(bg[k].y, r1.y, bg[k].z * r2.y)),
+                            fmaf(bg[k].x, r0.z, fmaf(bg[k].y, r1.z, bg[k].z * r2.z)));
             }
             const long long o_i = (long long)c * n_pts + i0;
             if constexpr (PTS == 4) {
@@ -472,6 +521,156 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
                 if (out_which) out_which[o_i] = bs[0];
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Configuration-major variant for RobotSDF-style batches (many joint configurations, shared points).
+//
+// Lanes of a warp are 32 CONFIGURATIONS of the same point instead of 32 points of the same configuration:
+// neighbouring configurations place every link almost identically, so (a) the prune / evaluate decisions of a
+// warp agree (the point-major kernel ran at 24/32 active lanes and evaluated nearly all 8 links per warp because
+// some lane always needed them), (b) the 32 table gathers of a warp instruction fall into a handful of cache lines
+// instead of 32, and (c) a cheap first-stage bound becomes worthwhile: the link's bounding sphere, carried into
+// the OBJECT frame once per (configuration, link), rejects a link with 9 instructions and without transforming
+// the point.  Results are bit-identical to the point-major kernel (same transform / lookup arithmetic; pruning is
+// exact).  A block owns a tile of 32 configurations x 32 points; results are transposed through shared memory so
+// that global stores stay coalesced along the point axis.
+constexpr int kCmCfg = 32;
+constexpr int kCmWarps = 8;
+constexpr int kCmPts = 4;                         // points per thread
+constexpr int kCmTilePts = kCmWarps * kCmPts;     // 32
+constexpr int kCmMaxS = 16;
+struct __align__(16) CmSmem {
+    float4 xf[kCmCfg][3 * kCmMaxS + 1];           // row stride = 49 float4: conflict-free LDS.128 across lanes
+    float4 sph[kCmCfg][kCmMaxS + 1];              // bounding sphere (object frame) per (cfg, link); stride 17
+    float4 out[kCmCfg][kCmTilePts + 1];           // {val, gx, gy, gz}; stride 33
+    int which[kCmCfg][kCmTilePts + 1];
+};
+
+__global__ void __launch_bounds__(kCmCfg * kCmWarps, 3)
+composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_sdf, const float *__restrict__ xforms,
+                         int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, long long n_pts,
+                         float *__restrict__ out_val, float *__restrict__ out_grad, int *__restrict__ out_which) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CmSmem &sm = *reinterpret_cast<CmSmem *>(smem_raw);
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.y * kCmCfg;                       // first configuration (relative to cfg_begin)
+    const int ncfg = min(kCmCfg, cfg_count - c0);
+    // ---- stage the transforms of this configuration tile and the object-frame bounding spheres ----
+    for (int item = threadIdx.x; item < kCmCfg * n_sdf; item += blockDim.x) {
+        const int ci = item % kCmCfg, s = item / kCmCfg;
+        const pvb_sdf_desc &d = descs.d[s];
+        float4 r0 = make_float4(1.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 1.f, 0.f, 0.f),
+               r2 = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (ci < ncfg) {
+            const float4 *row = reinterpret_cast<const float4 *>(xforms + ((size_t)s * n_cfg + cfg_begin + c0 + ci) * 16);
+            r0 = __ldg(row); r1 = __ldg(row + 1); r2 = __ldg(row + 2);
+        }
+        sm.xf[ci][3 * s] = r0; sm.xf[ci][3 * s + 1] = r1; sm.xf[ci][3 * s + 2] = r2;
+        // sphere around the link AABB, centre carried to the object frame: c_obj = R^T (c_link - t)
+        const f3 cl = mk3(0.5f * (d.bb_min[0] + d.bb_max[0]), 0.5f * (d.bb_min[1] + d.bb_max[1]),
+                          0.5f * (d.bb_min[2] + d.bb_max[2]));
+        const f3 hl = mk3(0.5f * (d.bb_max[0] - d.bb_min[0]), 0.5f * (d.bb_max[1] - d.bb_min[1]),
+                          0.5f * (d.bb_max[2] - d.bb_min[2]));
+        const f3 u = mk3(cl.x - r0.w, cl.y - r1.w, cl.z - r2.w);
+        const f3 co = mk3(r0.x * u.x + r1.x * u.y + r2.x * u.z, r0.y * u.x + r1.y * u.y + r2.y * u.z,
+                          r0.z * u.x + r1.z * u.y + r2.z * u.z);
+        float rad = sqrtf(hl.x * hl.x + hl.y * hl.y + hl.z * hl.z) * 1.0001f + 1e-6f;
+        // the bound needs an isometry: |R R^T - I| must vanish, otherwise this (cfg, link) never prunes in stage 1
+        const float e00 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z - 1.f, e11 = r1.x * r1.x + r1.y * r1.y + r1.z * r1.z - 1.f,
+                    e22 = r2.x * r2.x + r2.y * r2.y + r2.z * r2.z - 1.f;
+        const float e01 = r0.x * r1.x + r0.y * r1.y + r0.z * r1.z, e02 = r0.x * r2.x + r0.y * r2.y + r0.z * r2.z,
+                    e12 = r1.x * r2.x + r1.y * r2.y + r1.z * r2.z;
+        const float dev = fmaxf(fmaxf(fmaxf(fabsf(e00), fabsf(e11)), fmaxf(fabsf(e22), fabsf(e01))),
+                                fmaxf(fabsf(e02), fabsf(e12)));
+        const bool ok = d.kind == PVB_KIND_GRID && (d.flags & PVB_GRID_PRUNE_OK) && dev < 1e-5f;
+        if (!ok) rad = PVB_INF;
+        else rad += d.prune_margin;
+        sm.sph[ci][s] = make_float4(co.x, co.y, co.z, rad);
+    }
+    __syncthreads();
+    const bool lane_on = lane < ncfg;
+    const long long n_tiles = (n_pts + kCmTilePts - 1) / kCmTilePts;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long pt0 = tile * kCmTilePts + warp * kCmPts;
+        f3 p[kCmPts];
+        bool pon[kCmPts];
+#pragma unroll
+        for (int k = 0; k < kCmPts; ++k) {
+            pon[k] = lane_on && (pt0 + k < n_pts);
+            p[k] = (pt0 + k < n_pts) ? load_point(pts, pt0 + k) : mk3(0.f, 0.f, 0.f);
+        }
+        float best[kCmPts];
+        f3 bg[kCmPts];
+        int bs[kCmPts];
+#pragma unroll
+        for (int k = 0; k < kCmPts; ++k) { best[k] = PVB_INF; bg[k] = mk3(0.f, 0.f, 0.f); bs[k] = -1; }
+        for (int s = 0; s < n_sdf; ++s) {
+            const pvb_sdf_desc &d = descs.d[s];
+            const float4 sp = sm.sph[lane][s];
+            bool need[kCmPts];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < kCmPts; ++k) {
+                // stage 1: value >= |p - c_obj| - radius - margin (isometry); 0.9998 absorbs the 1e-5 non-rigidity
+                const float thr = best[k] + sp.w;
+                const float dx = p[k].x - sp.x, dy = p[k].y - sp.y, dz = p[k].z - sp.z;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                const bool pruned = bs[k] >= 0 && (thr < 0.f || d2 * 0.9998f > thr * thr);
+                need[k] = pon[k] && !pruned;
+                any |= need[k];
+            }
+            if (!any) continue;
+            const float4 r0 = sm.xf[lane][3 * s], r1 = sm.xf[lane][3 * s + 1], r2 = sm.xf[lane][3 * s + 2];
+            const bool prunable = d.kind == PVB_KIND_GRID && (d.flags & PVB_GRID_PRUNE_OK);
+#pragma unroll
+            for (int k = 0; k < kCmPts; ++k) {
+                if (!need[k]) continue;
+                // Transform3d.transform_points: R p + t  (sdf.py:399) -- same FMA order as the point-major kernel
+                const f3 q = mk3(fmaf(r0.x, p[k].x, fmaf(r0.y, p[k].y, fmaf(r0.z, p[k].z, r0.w))),
+                                 fmaf(r1.x, p[k].x, fmaf(r1.y, p[k].y, fmaf(r1.z, p[k].z, r1.w))),
+                                 fmaf(r2.x, p[k].x, fmaf(r2.y, p[k].y, fmaf(r2.z, p[k].z, r2.w))));
+                if (prunable && bs[k] >= 0) {     // stage 2: distance to the link AABB in the link frame
+                    const float thr = best[k] + d.prune_margin;
+                    const float ex = fmaxf(fmaxf(d.bb_min[0] - q.x, q.x - d.bb_max[0]), 0.f);
+                    const float ey = fmaxf(fmaxf(d.bb_min[1] - q.y, q.y - d.bb_max[1]), 0.f);
+                    const float ez = fmaxf(fmaxf(d.bb_min[2] - q.z, q.z - d.bb_max[2]), 0.f);
+                    if (thr < 0.f || ex * ex + ey * ey + ez * ez > thr * thr) continue;
+                }
+                SdfOut o;
+                if (d.kind == PVB_KIND_GRID) o = grid_eval<false, true>(d, st, q, 0u, 0ull, nullptr);
+                else o = sphere_eval(d.radius, q);
+                if (bs[k] < 0 || o.val < best[k] || (o.val == best[k] && s < bs[k])) {
+                    best[k] = o.val; bg[k] = o.grad; bs[k] = s;
+                }
+            }
+        }
+        // rotate the winning gradients back (g @ M[:3,:3]) and park the results for the transposed store
+#pragma unroll
+        for (int k = 0; k < kCmPts; ++k) {
+            const int sb = max(bs[k], 0);
+            const float4 r0 = sm.xf[lane][3 * sb], r1 = sm.xf[lane][3 * sb + 1], r2 = sm.xf[lane][3 * sb + 2];
+            const f3 go = mk3(fmaf(bg[k].x, r0.x, fmaf(bg[k].y, r1.x, bg[k].z * r2.x)),
+                              fmaf(bg[k].x, r0.y, fmaf(bg[k].y, r1.y, bg[k].z * r2.y)),
+                              fmaf(bg[k].x, r0.z, fmaf(bg[k].y, r1.z, bg[k].z * r2.z)));
+            sm.out[lane][warp * kCmPts + k] = make_float4(best[k], go.x, go.y, go.z);
+            if (out_which) sm.which[lane][warp * kCmPts + k] = bs[k];
+        }
+        __syncthreads();
+        // transposed store: one configuration row (32 consecutive points) per warp instruction
+        const long long pt = tile * kCmTilePts + lane;
+        if (pt < n_pts) {
+            for (int r = warp; r < ncfg; r += kCmWarps) {
+                const float4 v = sm.out[r][lane];
+                const long long o_i = (long long)(c0 + r) * n_pts + pt;
+                __stcs(out_val + o_i, v.x);
+                __stcs(out_grad + 3 * o_i, v.y); __stcs(out_grad + 3 * o_i + 1, v.z); __stcs(out_grad + 3 * o_i + 2, v.w);
+                if (out_which) out_which[o_i] = sm.which[r][lane];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -775,6 +974,28 @@ extern "C" int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int3
                      aligned16(out_which) && (n_pts % 4 == 0);
     const long long n_vec = vec ? n_pts : 0;
     int rc = PVB_OK;
+    static const int cfg_major = [] { const char *e = getenv("PVB_COMP_CFGMAJOR"); return e ? atoi(e) : 1; }();
+    if (cfg_major && !needs_mesh && n_sdf <= kCmMaxS && cfg_count >= 16) {
+        static const bool smem_ok = cudaFuncSetAttribute(composed_cfgmajor_kernel,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)sizeof(CmSmem)) == cudaSuccess;
+        if (!smem_ok) {
+            pvb_set_error("pvb_composed_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+            return PVB_ERR_CUDA;
+        }
+        DescPack<kCmMaxS> pack;
+        memcpy(pack.d, descs, sizeof(pvb_sdf_desc) * (size_t)n_sdf);
+        const int gy = (cfg_count + kCmCfg - 1) / kCmCfg;
+        const long long n_tiles = (n_pts + kCmTilePts - 1) / kCmTilePts;
+        long long gx = ((long long)sm_count() * 3 * 4 + gy - 1) / gy;     // ~4 waves of resident CTAs
+        if (gx > n_tiles) gx = n_tiles;
+        if (gx < 1) gx = 1;
+        dim3 grid((unsigned)gx, (unsigned)gy);
+        composed_cfgmajor_kernel<<<grid, kCmCfg * kCmWarps, sizeof(CmSmem), s>>>(
+            pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, out_val, out_grad, out_which);
+        PVB_CHECK_LAUNCH("pvb_composed_query(cfg-major)");
+        return PVB_OK;
+    }
 #define PVB_COMP(MESH, PTS, FIRST, N)                                                                              \
     (n_sdf <= 16 ? launch_composed<MESH, PTS, 16>(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, FIRST, N,  \
                                                   mesh_mode, out_val, out_grad, out_which, s)                      \

@@ -219,6 +219,20 @@ def test_robot_arm_batched_equals_looped(tmp_path):
         # the reference's own tolerances (tests/test_model_to_sdf.py:211-212): FK of one configuration and of the
         # batch may differ in the last bit of the transforms
         assert torch.allclose(v, all_val[i]) and torch.allclose(g, all_grad[i], atol=1e-6)
+    # configuration-major kernel (>= 16 configurations per launch) == point-major kernel (one configuration
+    # slab per launch), bit for bit, including the argmin index
+    s.set_joint_configuration(th)
+    v_all, g_all, w_all = s.sdf.query(pts, return_which=True)
+    for i in (0, 7, 19):
+        v1, g1, w1 = s.sdf.query(pts, cfg_begin=i, cfg_count=1, return_which=True)
+        sl = slice(i * len(pts), (i + 1) * len(pts))
+        assert torch.equal(v1, v_all[sl]) and torch.equal(g1, g_all[sl]) and torch.equal(w1, w_all[sl])
+    # ragged sizes: 17 configurations x 1001 points (partial configuration tile, partial point tile)
+    s.set_joint_configuration(th[:17])
+    vr, gr = s.sdf.query(pts[:1001])
+    for i in (0, 16):
+        v1, g1 = s.sdf.query(pts[:1001], cfg_begin=i, cfg_count=1)
+        assert torch.equal(v1, vr[i * 1001:(i + 1) * 1001]) and torch.equal(g1, gr[i * 1001:(i + 1) * 1001])
     # independent recomposition: per-link CachedSDF calls on explicitly transformed points, argmin in torch
     s.set_joint_configuration(th)
     M = s.object_to_link_frames.get_matrix().reshape(8, 20, 4, 4)
