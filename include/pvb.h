@@ -133,7 +133,11 @@ int pvb_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, int
  * out_normal[n*3] optional (NULL to skip). */
 int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_t n, uint32_t mode,
                    float *out_dist, float *out_grad, float *out_closest, int32_t *out_face,
-                   float *out_normal, void *stream);
+                   float *out_normal, void *workspace, int64_t workspace_bytes, void *stream);
+/* Optional DEVICE scratch for the tree-walk kernels (pvb_mesh_query, pvb_chamfer): with at least
+ * pvb_query_workspace(n) bytes, large batches are spatially binned (counting sort into Morton cells) and walked
+ * in that order, which keeps warps coherent; results land in the original slots.  0 / NULL = walk in input order. */
+int64_t pvb_query_workspace(int64_t n);
 
 /* ---- CachedSDF.__call__ (sdf.py:535-571) and outside_surface (sdf.py:593-602) ----
  * out_val / out_grad may be NULL when only occupancy is wanted; out_outside (uint8, 0/1)
@@ -166,7 +170,8 @@ int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_m
  * `obj` (grid / sphere). */
 int64_t pvb_chamfer_workspace(int64_t n_pts);
 int pvb_chamfer(const pvb_sdf_desc *obj, const float *world_to_object, int32_t n_tf,
-                const float *pts, int64_t n_pts, float scale, float *workspace, float *out, void *stream);
+                const float *pts, int64_t n_pts, float scale, float *workspace, float *out,
+                void *sort_workspace, int64_t sort_workspace_bytes, void *stream);
 
 /* ---- sample_mesh_points, sdf.py:650-658 (area-uniform surface samples) ----
  * verts64 DEVICE double[n_verts*3]; faces DEVICE int32[n_faces*3]; cum_counts DEVICE int64[n_faces]

@@ -87,7 +87,8 @@ _SIGNATURES = {
                                      ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)]),
     "pvb_mesh_query": (ctypes.c_int, [ctypes.POINTER(SdfDesc), ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                      ctypes.c_void_p, ctypes.c_void_p]),
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "pvb_query_workspace": (ctypes.c_int64, [ctypes.c_int64]),
     "pvb_grid_lookup": (ctypes.c_int, [ctypes.POINTER(SdfDesc), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
                                        ctypes.c_void_p]),
@@ -100,7 +101,7 @@ _SIGNATURES = {
     "pvb_chamfer_workspace": (ctypes.c_int64, [ctypes.c_int64]),
     "pvb_chamfer": (ctypes.c_int, [ctypes.POINTER(SdfDesc), ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
                                    ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
-                                   ctypes.c_void_p]),
+                                   ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "pvb_mesh_sample": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                        ctypes.c_int64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p]),
@@ -171,6 +172,12 @@ def as_f32_points(points, device):
     if p.shape[-1] != 3:
         raise ValueError(f"expected points with last dimension 3, got {tuple(points.shape)}")
     return p.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def query_workspace(n, device):
+    """Device scratch for the spatial binning of large tree-walk batches (None for small ones)."""
+    nbytes = int(lib().pvb_query_workspace(n))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes > 0 else None
 
 
 def deliver(t, device, dtype=None):

@@ -65,12 +65,15 @@ def batch_chamfer_dist(world_to_object: torch.tensor, model_points_world_frame_e
         L = nat.lib()
         out = torch.empty(B, dtype=torch.float32, device=dev)
         nblk = int(L.pvb_chamfer_workspace(n))
+        sort_ws = nat.query_workspace(n, dev) if desc.kind == nat.PVB_KIND_MESH else None
         done = 0
         while done < B:     # the kernel takes at most 65535 transforms per launch
             nb = min(B - done, 65535)
             ws = torch.empty(nb * nblk, dtype=torch.float32, device=dev)
             nat.check(L.pvb_chamfer(ctypes.byref(desc), nat.ptr(W[done:]), nb, nat.ptr(p), n, float(scale),
-                                    nat.ptr(ws), nat.ptr(out[done:]), nat.stream_ptr(dev)), "pvb_chamfer")
+                                    nat.ptr(ws), nat.ptr(out[done:]), nat.ptr(sort_ws),
+                                    sort_ws.numel() if sort_ws is not None else 0, nat.stream_ptr(dev)),
+                      "pvb_chamfer")
             done += nb
     return nat.deliver(out, out_device, out_dtype)
 

@@ -116,18 +116,111 @@ __device__ __forceinline__ f3 load_point(const float *__restrict__ pts, long lon
     return mk3(__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2));
 }
 
+// ===================================================== spatial binning of queries
+// A random query batch makes every lane of a warp walk a different part of the BVH: the first version of the mesh
+// kernel executed 64 000 warp-instructions per 32 queries (~10 % SIMT efficiency, profiles/README.md).  Large
+// batches are therefore binned into 64^3 Morton-ordered cells over the padded mesh AABB with a counting sort
+// (histogram by atomics, single-block scan, scatter) and the tree walk processes them in that order through an
+// index permutation; results are written to the original slots, so callers see no reordering.
+constexpr int kSortBits = 6;                               // per axis
+constexpr int kSortCells = 1 << (3 * kSortBits);           // 262144
+constexpr long long kSortMinPoints = 1 << 15;
+
+__device__ __forceinline__ uint32_t part1by2(uint32_t x) {  // spread the low 10 bits, two zeros between bits
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+
+struct SortFrame {           // cell = morton(quantise(((M p) - lo) * scale)); M optional (chamfer: first transform)
+    float lo[3], scale[3];
+    float xf[12];
+    int use_xf;
+};
+
+__device__ __forceinline__ uint32_t sort_cell(const SortFrame &f, f3 p) {
+    if (f.use_xf)
+        p = mk3(fmaf(f.xf[0], p.x, fmaf(f.xf[1], p.y, fmaf(f.xf[2], p.z, f.xf[3]))),
+                fmaf(f.xf[4], p.x, fmaf(f.xf[5], p.y, fmaf(f.xf[6], p.z, f.xf[7]))),
+                fmaf(f.xf[8], p.x, fmaf(f.xf[9], p.y, fmaf(f.xf[10], p.z, f.xf[11]))));
+    const float m = (float)((1 << kSortBits) - 1);
+    const uint32_t cx = (uint32_t)fminf(fmaxf((p.x - f.lo[0]) * f.scale[0], 0.f), m);   // NaN -> 0
+    const uint32_t cy = (uint32_t)fminf(fmaxf((p.y - f.lo[1]) * f.scale[1], 0.f), m);
+    const uint32_t cz = (uint32_t)fminf(fmaxf((p.z - f.lo[2]) * f.scale[2], 0.f), m);
+    return part1by2(cx) | (part1by2(cy) << 1) | (part1by2(cz) << 2);
+}
+
+__global__ void sort_hist_kernel(const SortFrame f, const float *__restrict__ pts, long long n, const float *xf_dev,
+                                 uint32_t *__restrict__ cell, uint32_t *__restrict__ hist) {
+    SortFrame fr = f;
+    if (xf_dev) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) fr.xf[e] = __ldg(xf_dev + e);
+    }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t c = sort_cell(fr, load_point(pts, i));
+        cell[i] = c;
+        atomicAdd(hist + c, 1u);
+    }
+}
+
+// exclusive scan of kSortCells counters in place, one block of 1024 threads (256 counters per thread)
+__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t *__restrict__ hist) {
+    __shared__ uint32_t warp_sum[32];
+    constexpr int per = kSortCells / 1024;
+    uint32_t *mine = hist + (size_t)threadIdx.x * per;
+    uint32_t s = 0;
+    for (int j = 0; j < per; ++j) s += mine[j];
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = warp_sum[threadIdx.x], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (threadIdx.x >= o) wi += t;
+        }
+        warp_sum[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = warp_sum[threadIdx.x >> 5] + (incl - s);
+    for (int j = 0; j < per; ++j) { const uint32_t c = mine[j]; mine[j] = run; run += c; }
+}
+
+__global__ void sort_scatter_kernel(const uint32_t *__restrict__ cell, long long n, uint32_t *__restrict__ offs,
+                                    uint32_t *__restrict__ perm) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        perm[atomicAdd(offs + cell[i], 1u)] = (uint32_t)i;
+}
+
+static size_t sort_workspace_bytes(long long n) {
+    return (size_t)kSortCells * 4 + (size_t)n * 8;       // counters | cell ids | permutation
+}
+
 // ================================================================ mesh query
 constexpr int kMeshThreads = 256;
 
 __global__ void __launch_bounds__(kMeshThreads)
-mesh_query_kernel(const pvb_sdf_desc m, const float *__restrict__ pts, long long n, uint32_t mode, int n_stage_max,
-                  float *__restrict__ out_dist, float *__restrict__ out_grad, float *__restrict__ out_closest,
+mesh_query_kernel(const pvb_sdf_desc m, const float *__restrict__ pts, long long n,
+                  const uint32_t *__restrict__ perm, uint32_t mode, int n_stage_max, float *__restrict__ out_dist, float *__restrict__ out_grad, float *__restrict__ out_closest,
                   int *__restrict__ out_face, float *__restrict__ out_normal) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     const NodeStage st = stage_nodes(m.nodes, m.n_nodes, n_stage_max, smem_raw, &bar);
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const long long i = perm ? (long long)perm[j] : j;      // spatially binned order, original slot
         const f3 p = load_point(pts, i);
         f3 q;
         int face;
@@ -683,7 +776,8 @@ constexpr int kChamThreads = 256;
 
 __global__ void __launch_bounds__(kChamThreads)
 chamfer_partial_kernel(const pvb_sdf_desc obj, const float *__restrict__ w2o, const float *__restrict__ pts,
-                       long long n_pts, float scale, int n_stage_max, float *__restrict__ partial) {
+                       long long n_pts, const uint32_t *__restrict__ perm, float scale, int n_stage_max,
+                       float *__restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ float s_red[kChamThreads / 32];
@@ -695,7 +789,8 @@ chamfer_partial_kernel(const pvb_sdf_desc obj, const float *__restrict__ w2o, co
     for (int e = 0; e < 12; ++e) xf[e] = __ldg(W + e);
     float acc = 0.f;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_pts; j += stride) {
+        const long long i = perm ? (long long)perm[j] : j;
         const f3 p = load_point(pts, i);
         const f3 q = mk3(fmaf(xf[0], p.x, fmaf(xf[1], p.y, fmaf(xf[2], p.z, xf[3]))),
                          fmaf(xf[4], p.x, fmaf(xf[5], p.y, fmaf(xf[6], p.z, xf[7]))),
@@ -832,8 +927,50 @@ static int check_mesh(const pvb_sdf_desc *m, const char *who) {
     return PVB_OK;
 }
 
+// Bins `n` points (optionally seen through the rigid transform xf_dev) over the padded AABB of `obj`; returns the
+// permutation inside `workspace` or nullptr when the batch is small / no workspace was given.
+static const uint32_t *sort_queries(const pvb_sdf_desc *obj, const float *pts, long long n, const float *xf_dev,
+                                    void *workspace, size_t workspace_bytes, cudaStream_t stream, int *rc) {
+    *rc = PVB_OK;
+    static const int enabled = [] { const char *e = getenv("PVB_SORT_QUERIES"); return e ? atoi(e) : 1; }();
+    if (!enabled || !workspace || n < kSortMinPoints || n >= (1ll << 32) || workspace_bytes < sort_workspace_bytes(n))
+        return nullptr;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(workspace);
+    uint32_t *cell = hist + kSortCells;
+    uint32_t *perm = cell + n;
+    SortFrame f;
+    for (int a = 0; a < 3; ++a) {
+        const float ext = obj->bb_max[a] - obj->bb_min[a];
+        const float pad = 0.5f * ext + 1e-6f;                 // queries beyond the padded box clamp to the border cells
+        f.lo[a] = obj->bb_min[a] - pad;
+        f.scale[a] = (float)(1 << kSortBits) / (ext + 2.f * pad);
+    }
+    f.use_xf = xf_dev != nullptr;
+    for (int e = 0; e < 12; ++e) f.xf[e] = 0.f;
+    if (cudaMemsetAsync(hist, 0, (size_t)kSortCells * 4, stream) != cudaSuccess) {
+        pvb_set_error("sort_queries: cudaMemsetAsync failed");
+        *rc = PVB_ERR_CUDA;
+        return nullptr;
+    }
+    const int blocks = grid_for(n, 256, 8);
+    sort_hist_kernel<<<blocks, 256, 0, stream>>>(f, pts, n, xf_dev, cell, hist);
+    sort_scan_kernel<<<1, 1024, 0, stream>>>(hist);
+    sort_scatter_kernel<<<blocks, 256, 0, stream>>>(cell, n, hist, perm);
+    if (cudaGetLastError() != cudaSuccess) {
+        pvb_set_error("sort_queries: launch failed");
+        *rc = PVB_ERR_CUDA;
+        return nullptr;
+    }
+    return perm;
+}
+
+extern "C" int64_t pvb_query_workspace(int64_t n) {
+    return n >= kSortMinPoints ? (int64_t)sort_workspace_bytes(n) : 0;
+}
+
 extern "C" int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_t n, uint32_t mode, float *out_dist,
-                              float *out_grad, float *out_closest, int32_t *out_face, float *out_normal, void *stream) {
+                              float *out_grad, float *out_closest, int32_t *out_face, float *out_normal,
+                              void *workspace, int64_t workspace_bytes, void *stream) {
     if (!mesh || n < 0 || (n > 0 && (!pts || !out_dist || !out_grad))) {
         pvb_set_error("pvb_mesh_query: null argument");
         return PVB_ERR_INVALID;
@@ -855,8 +992,12 @@ extern "C" int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_
         pvb_set_error("pvb_mesh_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
         return PVB_ERR_CUDA;
     }
+    int rc = PVB_OK;
+    const uint32_t *perm = sort_queries(mesh, pts, n, nullptr, workspace, (size_t)(workspace_bytes < 0 ? 0 : workspace_bytes),
+                                        (cudaStream_t)stream, &rc);
+    if (rc != PVB_OK) return rc;
     const int blocks = grid_for(n, kMeshThreads, 8);
-    mesh_query_kernel<<<blocks, kMeshThreads, smem, (cudaStream_t)stream>>>(*mesh, pts, n, mode, n_stage, out_dist,
+    mesh_query_kernel<<<blocks, kMeshThreads, smem, (cudaStream_t)stream>>>(*mesh, pts, n, perm, mode, n_stage, out_dist,
                                                                             out_grad, out_closest, out_face, out_normal);
     PVB_CHECK_LAUNCH("pvb_mesh_query");
     return PVB_OK;
@@ -1017,7 +1158,8 @@ extern "C" int64_t pvb_chamfer_workspace(int64_t n_pts) {
 }
 
 extern "C" int pvb_chamfer(const pvb_sdf_desc *obj, const float *world_to_object, int32_t n_tf, const float *pts,
-                           int64_t n_pts, float scale, float *workspace, float *out, void *stream) {
+                           int64_t n_pts, float scale, float *workspace, float *out, void *sort_workspace,
+                           int64_t sort_workspace_bytes, void *stream) {
     if (!obj || !world_to_object || n_tf < 0 || n_pts < 1 || !pts || !workspace || !out) {
         pvb_set_error("pvb_chamfer: invalid argument");
         return PVB_ERR_INVALID;
@@ -1036,9 +1178,17 @@ extern "C" int pvb_chamfer(const pvb_sdf_desc *obj, const float *world_to_object
         pvb_set_error("pvb_chamfer: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
         return PVB_ERR_CUDA;
     }
+    int rc = PVB_OK;
+    // the cloud is binned in the object frame of the FIRST transform; the others are rigid too, so locality carries over
+    const uint32_t *perm = obj->kind == PVB_KIND_MESH
+                               ? sort_queries(obj, pts, n_pts, world_to_object, sort_workspace,
+                                              (size_t)(sort_workspace_bytes < 0 ? 0 : sort_workspace_bytes),
+                                              (cudaStream_t)stream, &rc)
+                               : nullptr;
+    if (rc != PVB_OK) return rc;
     dim3 grid((unsigned)n_blk, (unsigned)n_tf);
     chamfer_partial_kernel<<<grid, kChamThreads, (size_t)n_stage * 128, (cudaStream_t)stream>>>(
-        *obj, world_to_object, pts, n_pts, scale, n_stage, workspace);
+        *obj, world_to_object, pts, n_pts, perm, scale, n_stage, workspace);
     PVB_CHECK_LAUNCH("pvb_chamfer(partial)");
     chamfer_finish_kernel<<<n_tf, 32, 0, (cudaStream_t)stream>>>(workspace, n_blk, n_pts, out);
     PVB_CHECK_LAUNCH("pvb_chamfer(finish)");

@@ -231,8 +231,10 @@ class ObjectFactory(abc.ABC):
             closest = torch.empty(n, 3, dtype=torch.float32, device=device)
             normal = torch.empty(n, 3, dtype=torch.float32, device=device) if compute_normal else None
             desc = self.native_desc(device)
+            ws = nat.query_workspace(n, device)
             nat.check(nat.lib().pvb_mesh_query(ctypes.byref(desc), nat.ptr(p), n, mode, nat.ptr(dist), nat.ptr(grad),
-                                               nat.ptr(closest), None, nat.ptr(normal), nat.stream_ptr(device)),
+                                               nat.ptr(closest), None, nat.ptr(normal), nat.ptr(ws),
+                                               ws.numel() if ws is not None else 0, nat.stream_ptr(device)),
                       "pvb_mesh_query")
 
         def fin(t, tail):

@@ -30,7 +30,7 @@ def test_c_abi_exports_every_declared_symbol(built_lib):
 def test_c_abi_argument_validation_without_gpu(built_lib):
     from pytorch_volumetric_b200 import _native
     d = _native.SdfDesc()
-    rc = built_lib.pvb_mesh_query(ctypes.byref(d), None, 10, 3, None, None, None, None, None, None)
+    rc = built_lib.pvb_mesh_query(ctypes.byref(d), None, 10, 3, None, None, None, None, None, None, 0, None)
     assert rc == -1 and b"null" in built_lib.pvb_last_error()
     rc = built_lib.pvb_grid_lookup(ctypes.byref(d), ctypes.c_void_p(16), 10, None, None, None, 0.0, None, None)
     assert rc == -1 and b"empty" in built_lib.pvb_last_error()
