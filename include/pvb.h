@@ -46,8 +46,11 @@ enum {
                                       default is fp64, the dtype torch infers for numpy ranges */
     PVB_GRID_OOB_GT     = 1u << 1, /* OutOfBoundsStrategy.LOOKUP_GT_SDF: out-of-range points take the
                                       mesh query (mesh fields must be filled); default BOUNDING_BOX */
-    PVB_GRID_PRUNE_OK   = 1u << 2  /* table verified to satisfy val >= dist(voxel centre, bb): composed
-                                      kernels may skip lookups that provably cannot win the min */
+    PVB_GRID_PRUNE_OK   = 1u << 2, /* table verified to satisfy val >= dist(voxel centre, bb) - prune_margin:
+                                      composed kernels may skip lookups that provably cannot win the min */
+    PVB_MESH_CLOSED     = 1u << 3  /* every directed edge is matched by its reverse (closed, consistently oriented
+                                      surface): crossing parity is direction independent, so the sign test may use
+                                      the exact axis-aligned walk instead of the reference's diagonal ray */
 };
 
 /* pvb_mesh_query mode flags */

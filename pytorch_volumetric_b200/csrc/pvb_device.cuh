@@ -232,6 +232,93 @@ __device__ __forceinline__ int bvh_parity(const float4 *__restrict__ gnodes, con
 }
 
 // ----------------------------------------------------------------------------
+// Crossing parity along +x for CLOSED meshes (every directed edge matched by its reverse, checked on the host).
+// The parity of a closed surface does not depend on the ray direction, so the reference's diagonal ray
+// (sdf.py:147-153) can be replaced by the axis through the query point: the box test becomes an exact 2-D
+// containment (no slabs, no divisions), the triangle test loses the shear, and far fewer nodes are visited.
+// Exactness: same translated-vertex edge functions as above (shared edges antisymmetric by construction); an edge
+// function that is exactly zero is resolved by symbolic perturbation of the origin by (eps, eps^2) in (y, z) --
+// sign of dU/dy, then dU/dz, both exact coordinate comparisons -- so that a ray through an edge or a vertex is
+// counted by exactly one of the adjacent triangles and tangential contacts cancel.
+__device__ __forceinline__ float edge_sign_x(float By, float Bz, float Cy, float Cz, float vBy, float vBz, float vCy,
+                                             float vCz) {
+    // U = Cy' * Bz' - Cz' * By' with primes = translated by the origin; exact sign
+    float U = __fsub_rn(__fmul_rn(Cy, Bz), __fmul_rn(Cz, By));
+    if (U == 0.f) {
+        const double Ud = (double)Cy * (double)Bz - (double)Cz * (double)By;
+        if (Ud != 0.0) U = Ud > 0.0 ? 1.f : -1.f;
+        else {
+            // dU/dPy = Cz - Bz, dU/dPz = By - Cy (untranslated vertex coordinates: exact comparisons)
+            if (vCz != vBz) U = vCz > vBz ? 1.f : -1.f;
+            else U = vBy > vCy ? 1.f : (vBy < vCy ? -1.f : 0.f);
+        }
+    }
+    return U;
+}
+
+__device__ __forceinline__ int bvh_parity_x(const float4 *__restrict__ gnodes, const NodeStage &st,
+                                            const float4 *__restrict__ tris, f3 o) {
+    int hits = 0;
+    int stack_n[kStack];
+    int sp = 0;
+    stack_n[sp++] = 0;
+    while (sp > 0) {
+        const int ni = stack_n[--sp];
+        const float4 *n = node_ptr(gnodes, st, ni);
+        const float4 loy = n[1], loz = n[2], hix = n[3], hiy = n[4], hiz = n[5];
+        const int4 ch = *reinterpret_cast<const int4 *>(n + 6);
+        const float ly[4] = {loy.x, loy.y, loy.z, loy.w}, lz[4] = {loz.x, loz.y, loz.z, loz.w};
+        const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w},
+                    hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
+        const int c[4] = {ch.x, ch.y, ch.z, ch.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // exact: a triangle crossed at t >= 0 has the crossing point inside its box
+            const bool in = (c[k] != INT32_MIN) & (o.y >= ly[k]) & (o.y <= hy[k]) & (o.z >= lz[k]) & (o.z <= hz[k]) &
+                            (hx[k] >= o.x);
+            if (!in) continue;
+            if (c[k] >= 0) {
+                if (sp < kStack) stack_n[sp++] = c[k];
+                continue;
+            }
+            const unsigned code = (unsigned)~c[k];
+            const int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
+            for (int t = first; t < first + cnt; ++t) {
+                const float4 v0 = __ldg(tris + 3 * (size_t)t);
+                const float4 v1 = __ldg(tris + 3 * (size_t)t + 1);
+                const float4 v2 = __ldg(tris + 3 * (size_t)t + 2);
+                const float Ay = v0.y - o.y, Az = v0.z - o.z, By = v1.y - o.y, Bz = v1.z - o.z, Cy = v2.y - o.y,
+                            Cz = v2.z - o.z;
+                const float U = edge_sign_x(By, Bz, Cy, Cz, v1.y, v1.z, v2.y, v2.z);
+                const float V = edge_sign_x(Cy, Cz, Ay, Az, v2.y, v2.z, v0.y, v0.z);
+                const float W = edge_sign_x(Ay, Az, By, Bz, v0.y, v0.z, v1.y, v1.z);
+                if ((U < 0.f || V < 0.f || W < 0.f) && (U > 0.f || V > 0.f || W > 0.f)) continue;
+                if (U == 0.f && V == 0.f && W == 0.f) continue;       // degenerate in projection (edge-on triangle)
+                // x of the crossing relative to the origin, in exact-sign arithmetic where it matters
+                const double Ud = (double)__fsub_rn(__fmul_rn(Cy, Bz), __fmul_rn(Cz, By));
+                const double Vd = (double)__fsub_rn(__fmul_rn(Ay, Cz), __fmul_rn(Az, Cy));
+                const double Wd = (double)__fsub_rn(__fmul_rn(By, Az), __fmul_rn(Bz, Ay));
+                const double det = Ud + Vd + Wd;
+                const double T = Ud * (double)(v0.x - o.x) + Vd * (double)(v1.x - o.x) + Wd * (double)(v2.x - o.x);
+                if (det == 0.0) {
+                    // barycentric weights vanished in fp32 although the signs are decided: fall back to the plane
+                    // through the three translated vertices evaluated in fp64
+                    const double ux = (double)v1.x - v0.x, uy = (double)v1.y - v0.y, uz = (double)v1.z - v0.z;
+                    const double wx = (double)v2.x - v0.x, wy = (double)v2.y - v0.y, wz = (double)v2.z - v0.z;
+                    const double nx = uy * wz - uz * wy, ny = uz * wx - ux * wz, nz = ux * wy - uy * wx;
+                    if (nx == 0.0) continue;
+                    const double tx = (nx * ((double)v0.x - o.x) + ny * ((double)v0.y - o.y) + nz * ((double)v0.z - o.z)) / nx;
+                    if (tx >= 0.0) ++hits;
+                    continue;
+                }
+                if ((det > 0.0) ? (T >= 0.0) : (T <= 0.0)) ++hits;
+            }
+        }
+    }
+    return hits & 1;
+}
+
+// ----------------------------------------------------------------------------
 // Deterministic stand-in for the reference's unseeded ray jitter (sdf.py:149):
 // three ~N(0,1) numbers per point from an integer hash (sum of four 16-bit
 // uniforms), every step exact in fp32 so that a host mirror reproduces it.
@@ -265,7 +352,10 @@ __device__ __forceinline__ SdfOut mesh_eval(const pvb_sdf_desc &m, const NodeSta
         const f3 dir = mk3(fmaf(1e-4f, hash_normal(m.ray_seed, idx, 0), m.ray_far[0]),
                            fmaf(1e-4f, hash_normal(m.ray_seed, idx, 1), m.ray_far[1]),
                            fmaf(1e-4f, hash_normal(m.ray_seed, idx, 2), m.ray_far[2]));
-        inside = bvh_parity(nodes, st, tris, p, dir) != 0;
+        // closed mesh: any direction gives the same parity -> exact axis-aligned walk; otherwise the reference's
+        // own direction rule, because on an open surface the answer depends on it
+        inside = (m.flags & PVB_MESH_CLOSED) ? bvh_parity_x(nodes, st, tris, p) != 0
+                                             : bvh_parity(nodes, st, tris, p, dir) != 0;
     }
     if (inside) dist = -dist;                                  // sdf.py:155
     else { g.x = -g.x; g.y = -g.y; g.z = -g.z; }               // sdf.py:157

@@ -195,6 +195,9 @@ class ObjectFactory(abc.ABC):
         self._fill_mesh_part(d, st)
         return d
 
+    #: set False to force the reference's diagonal ray (sdf.py:147-153) even on closed meshes
+    axis_ray_when_closed = True
+
     def _fill_mesh_part(self, d, st):
         d.nodes = st["nodes"].data_ptr()
         d.n_nodes = st["nodes"].shape[0]
@@ -208,6 +211,8 @@ class ObjectFactory(abc.ABC):
             d.bb_min[k] = float(np.float32(bb[k, 0]))
             d.bb_max[k] = float(np.float32(bb[k, 1]))
         d.ray_seed = self.ray_seed & 0xFFFFFFFF
+        if self.axis_ray_when_closed and self.is_closed:
+            d.flags |= nat.PVB_MESH_CLOSED
 
     # -- the query (sdf.py:122-172) ----------------------------------------------
     def _do_object_frame_closest_point(self, points_in_object_frame, compute_normal=False, device=None,
@@ -667,6 +672,7 @@ class CachedSDF(ObjectFrameSDF):
             if gt_native is not None:
                 flags |= nat.PVB_GRID_OOB_GT
                 self.gt_sdf.obj_factory._fill_mesh_part(d, self.gt_sdf.obj_factory._device_state(self._cdev))
+                flags |= d.flags & nat.PVB_MESH_CLOSED
                 for k in range(3):       # _fill_mesh_part rewrote the box from the mesh; keep self.bb
                     d.bb_min[k] = float(bb[k, 0])
                     d.bb_max[k] = float(bb[k, 1])
