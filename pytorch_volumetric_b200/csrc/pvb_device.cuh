@@ -12,7 +12,7 @@
 namespace pvb {
 
 constexpr int kStack = 40;            // traversal stack entries per thread (builder bounds depth)
-#define PVB_INF __int_as_float(0x7f800000)
+#define PVB_INF (__builtin_huge_valf())
 
 struct f3 { float x, y, z; };
 __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -337,18 +337,27 @@ struct SdfOut { float val; f3 grad; };
 
 // MeshSDF value + gradient for one point (sdf.py:139-164).
 //   mode: PVB_MESH_* flags.  `idx` seeds the ray jitter.
+//   init_d2: squared search radius (PVB_INF for an unconditional query); when nothing lies within it, *face_out
+//   is -1 and the returned value is meaningless.  known_outside: the caller has proven the point outside the
+//   surface (outside the AABB of a closed mesh), so the parity walk is skipped.
 __device__ __forceinline__ SdfOut mesh_eval(const pvb_sdf_desc &m, const NodeStage &st, f3 p, uint32_t mode,
-                                            uint64_t idx, f3 *closest_out, int *face_out) {
+                                            uint64_t idx, f3 *closest_out, int *face_out, float init_d2 = PVB_INF,
+                                            bool known_outside = false) {
     const float4 *nodes = reinterpret_cast<const float4 *>(m.nodes);
     const float4 *tris = reinterpret_cast<const float4 *>(m.tris);
-    const Closest c = bvh_closest(nodes, st, tris, p, PVB_INF);
+    const Closest c = bvh_closest(nodes, st, tris, p, init_d2);
+    if (c.face < 0) {
+        if (face_out) *face_out = -1;
+        SdfOut none; none.val = PVB_INF; none.grad = mk3(0.f, 0.f, 0.f);
+        return none;
+    }
     f3 g = c.q - p;                                            // sdf.py:139
     float dist = sqrtf(fmaf(g.x, g.x, fmaf(g.y, g.y, g.z * g.z)));   // sdf.py:141
     if (dist > 0.f) {                                          // sdf.py:143-144
         g.x = __fdiv_rn(g.x, dist); g.y = __fdiv_rn(g.y, dist); g.z = __fdiv_rn(g.z, dist);
     }
     bool inside = false;
-    if (mode & PVB_MESH_SIGNED) {                              // sdf.py:146-154
+    if ((mode & PVB_MESH_SIGNED) && !known_outside) {          // sdf.py:146-154
         const f3 dir = mk3(fmaf(1e-4f, hash_normal(m.ray_seed, idx, 0), m.ray_far[0]),
                            fmaf(1e-4f, hash_normal(m.ray_seed, idx, 1), m.ray_far[1]),
                            fmaf(1e-4f, hash_normal(m.ray_seed, idx, 2), m.ray_far[2]));

@@ -522,8 +522,25 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
                 SdfOut o;
                 const uint64_t idx = ((uint64_t)c * (uint64_t)n_pts + (uint64_t)(i0 + k)) * (uint64_t)n_sdf + (uint64_t)s;
                 if (d.kind == PVB_KIND_GRID) o = grid_eval<kMesh, true>(d, st, q, mesh_mode, idx, nullptr);
-                else if (kMesh && d.kind == PVB_KIND_MESH) o = mesh_eval(d, st, q, mesh_mode, idx, nullptr, nullptr);
-                else o = sphere_eval(d.radius, q);
+                else if (kMesh && d.kind == PVB_KIND_MESH) {
+                    // closed mesh, query outside its AABB: the value is +distance >= dist(q, AABB), so (a) skip it
+                    // when that bound already exceeds the running min, (b) otherwise search only within the
+                    // running min and (c) skip the parity walk -- all exact
+                    float init_d2 = PVB_INF;
+                    bool outside_box = false;
+                    if ((d.flags & PVB_MESH_CLOSED) && (mesh_mode & PVB_MESH_SIGNED)) {
+                        const float lb2 = aabb_lb2(d, q);
+                        outside_box = lb2 > 0.f;
+                        if (outside_box && bs[k] >= 0) {
+                            const float thr = best[k] + d.prune_margin;
+                            if (thr < 0.f || lb2 > thr * thr) return;
+                            if (best[k] > 0.f) init_d2 = thr * thr;
+                        }
+                    }
+                    int face;
+                    o = mesh_eval(d, st, q, mesh_mode, idx, nullptr, &face, init_d2, outside_box);
+                    if (face < 0) return;          // nothing within the running min: cannot be the argmin
+                } else o = sphere_eval(d.radius, q);
                 // torch.argmin semantics (sdf.py:421): smallest value, first index on ties -- whatever the visiting order
                 if (bs[k] < 0 || o.val < best[k] || (o.val == best[k] && s < bs[k])) {
                     best[k] = o.val; bg[k] = o.grad; bs[k] = s;

@@ -213,6 +213,8 @@ class ObjectFactory(abc.ABC):
         d.ray_seed = self.ray_seed & 0xFFFFFFFF
         if self.axis_ray_when_closed and self.is_closed:
             d.flags |= nat.PVB_MESH_CLOSED
+        # slack of the "value >= distance to the AABB" bound used by the composed kernels (fp32 rounding only)
+        d.prune_margin = 1e-5 * max(1.0, float(np.abs(bb).max()))
 
     # -- the query (sdf.py:122-172) ----------------------------------------------
     def _do_object_frame_closest_point(self, points_in_object_frame, compute_normal=False, device=None,
