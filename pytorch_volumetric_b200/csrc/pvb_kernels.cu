@@ -213,25 +213,42 @@ constexpr int kMeshThreads = 256;
 
 __global__ void __launch_bounds__(kMeshThreads)
 mesh_query_kernel(const pvb_sdf_desc m, const float *__restrict__ pts, long long n,
-                  const uint32_t *__restrict__ perm, uint32_t mode, int n_stage_max, float *__restrict__ out_dist, float *__restrict__ out_grad, float *__restrict__ out_closest,
+                  const uint32_t *__restrict__ perm, int run, uint32_t mode, int n_stage_max, float *__restrict__ out_dist, float *__restrict__ out_grad, float *__restrict__ out_closest,
                   int *__restrict__ out_face, float *__restrict__ out_normal) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     const NodeStage st = stage_nodes(m.nodes, m.n_nodes, n_stage_max, smem_raw, &bar);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const long long i = perm ? (long long)perm[j] : j;      // spatially binned order, original slot
-        const f3 p = load_point(pts, i);
-        f3 q;
-        int face;
-        const SdfOut o = mesh_eval(m, st, p, mode, (uint64_t)i, &q, &face);
-        out_dist[i] = o.val;
-        out_grad[3 * i] = o.grad.x; out_grad[3 * i + 1] = o.grad.y; out_grad[3 * i + 2] = o.grad.z;
-        if (out_closest) { out_closest[3 * i] = q.x; out_closest[3 * i + 1] = q.y; out_closest[3 * i + 2] = q.z; }
-        if (out_face) out_face[i] = face;
-        if (out_normal) {
-            const float *fn = m.face_normals + 3 * (size_t)max(face, 0);
-            out_normal[3 * i] = __ldg(fn); out_normal[3 * i + 1] = __ldg(fn + 1); out_normal[3 * i + 2] = __ldg(fn + 2);
+    // Each thread owns runs of `run` CONSECUTIVE queries of the (binned) order: the closest point of the previous
+    // query lies on the surface, so its distance to the next query bounds that query's answer from above and the
+    // walk starts with a tight radius instead of infinity (neighbouring queries are centimetres apart).
+    const long long threads = (long long)gridDim.x * blockDim.x;
+    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * run; base < n; base += threads * run) {
+        f3 prev_q = mk3(0.f, 0.f, 0.f);
+        bool have_prev = false;
+        for (int r = 0; r < run; ++r) {
+            const long long j = base + r;
+            if (j >= n) break;
+            const long long i = perm ? (long long)perm[j] : j;      // spatially binned order, original slot
+            const f3 p = load_point(pts, i);
+            float init_d2 = PVB_INF;
+            if (have_prev) {
+                const f3 e = prev_q - p;
+                init_d2 = dot(e, e) * 1.0001f + 1e-12f;
+            }
+            f3 q;
+            int face;
+            SdfOut o = mesh_eval(m, st, p, mode, (uint64_t)i, &q, &face, init_d2);
+            if (face < 0) o = mesh_eval(m, st, p, mode, (uint64_t)i, &q, &face);   // rounding: retry unbounded
+            prev_q = q;
+            have_prev = true;
+            out_dist[i] = o.val;
+            out_grad[3 * i] = o.grad.x; out_grad[3 * i + 1] = o.grad.y; out_grad[3 * i + 2] = o.grad.z;
+            if (out_closest) { out_closest[3 * i] = q.x; out_closest[3 * i + 1] = q.y; out_closest[3 * i + 2] = q.z; }
+            if (out_face) out_face[i] = face;
+            if (out_normal) {
+                const float *fn = m.face_normals + 3 * (size_t)max(face, 0);
+                out_normal[3 * i] = __ldg(fn); out_normal[3 * i + 1] = __ldg(fn + 1); out_normal[3 * i + 2] = __ldg(fn + 2);
+            }
         }
     }
 }
@@ -1013,9 +1030,14 @@ extern "C" int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_
     const uint32_t *perm = sort_queries(mesh, pts, n, nullptr, workspace, (size_t)(workspace_bytes < 0 ? 0 : workspace_bytes),
                                         (cudaStream_t)stream, &rc);
     if (rc != PVB_OK) return rc;
-    const int blocks = grid_for(n, kMeshThreads, 8);
-    mesh_query_kernel<<<blocks, kMeshThreads, smem, (cudaStream_t)stream>>>(*mesh, pts, n, perm, mode, n_stage, out_dist,
-                                                                            out_grad, out_closest, out_face, out_normal);
+    // run length: long enough to amortise the bound, short enough to keep every SM full
+    static const int run_max = [] { const char *e = getenv("PVB_MESH_RUN"); return e ? atoi(e) : 8; }();
+    long long run = n / ((long long)sm_count() * 2048);
+    run = run < 1 ? 1 : (run > run_max ? run_max : run);
+    const int blocks = grid_for((n + run - 1) / run, kMeshThreads, 8);
+    mesh_query_kernel<<<blocks, kMeshThreads, smem, (cudaStream_t)stream>>>(*mesh, pts, n, perm, (int)run, mode, n_stage,
+                                                                            out_dist, out_grad, out_closest, out_face,
+                                                                            out_normal);
     PVB_CHECK_LAUNCH("pvb_mesh_query");
     return PVB_OK;
 }
