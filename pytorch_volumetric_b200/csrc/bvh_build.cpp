@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <climits>
 #include <queue>
 #include <vector>
@@ -36,7 +37,7 @@ struct BinNode {
     int start = 0, count = 0;
 };
 
-constexpr int kLeafMax = 4;
+static int kLeafMax = 4;   // triangles per leaf, 1..4 (PVB_BVH_LEAF; the link encoding holds count-1 in 2 bits)
 constexpr int kBins = 16;
 
 struct Builder {
@@ -148,6 +149,10 @@ extern "C" int pvb_bvh_build(const float *verts, int64_t n_verts, const int32_t 
             return PVB_ERR_INVALID;
         }
 
+    if (const char *e = getenv("PVB_BVH_LEAF")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 4) kLeafMax = v;
+    }
     Builder b;
     b.verts = verts; b.faces = faces;
     b.tbox.resize((size_t)n_faces);
