@@ -183,6 +183,9 @@ class C2(Workload):
         cache = os.path.join(cache_dir or tempfile.gettempdir(), f"pvb_bench_c2_{rank}.pkl")
         self.sdf = pv.CachedSDF("drill", 0.005, self.obj.bounding_box(padding=0.1), gt, device="cuda",
                                 cache_path=cache, clean_cache=True)
+        # same object for host callers: results come back as host tensors (tables still live on the GPU)
+        self.sdf_host = pv.CachedSDF("drill", 0.005, self.obj.bounding_box(padding=0.1), gt, device="cpu",
+                                     cache_path=cache)
         lo = np.array([r[0] for r in self.sdf.ranges]); hi = np.array([r[1] for r in self.sdf.ranges])
         self.lo, self.hi = lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo)
         self.host = [workloads.uniform_points(self.n_points, self.lo, self.hi, seed=1000 * rank + b).pin_memory()
@@ -204,7 +207,8 @@ class C2(Workload):
         return self.sdf(self.dev[i % len(self.dev)])
 
     def step_host(self, i):
-        return self.sdf(self.host[i % len(self.host)])
+        # public API, host tensor in -> host tensors out (the reference's own default is device="cpu")
+        return self.sdf_host(self.host[i % len(self.host)])
 
     # CPU arm: the oracle port on the same tables
     def cpu_setup(self):

@@ -725,10 +725,80 @@ class CachedSDF(ObjectFrameSDF):
                                                 nat.stream_ptr(device)), "pvb_grid_lookup")
         return p, val, grad, outside, index
 
+    #: host batches at least this large are streamed through the GPU in chunks (copy-in / lookup / copy-out
+    #: overlapped on three streams); smaller ones take one H2D copy, one launch, one D2H copy
+    host_pipeline_min_points = 1 << 21
+    host_pipeline_chunk = 1 << 20
+
+    def _host_pipeline(self, points):
+        """Host tensor in, pinned host tensors out, PCIe busy in both directions at once.
+
+        Chunk i is copied in on `s_in` while chunk i-1 is looked up on the current stream and chunk i-2 is copied
+        out on `s_out`; two device slots per direction, events order the reuse of a slot."""
+        device = self._cdev
+        src = points.detach().reshape(-1, 3)
+        if src.dtype != torch.float32:
+            src = src.float()
+        src = src.contiguous()
+        n = src.shape[0]
+        C = self.host_pipeline_chunk
+        with torch.cuda.device(device):
+            cur = torch.cuda.current_stream(device)
+            st = getattr(self, "_pipe_state", None)
+            if st is None:
+                st = {"s_in": torch.cuda.Stream(device), "s_out": torch.cuda.Stream(device),
+                      "d_in": [torch.empty(C, 3, dtype=torch.float32, device=device) for _ in range(2)],
+                      "d_val": [torch.empty(C, dtype=torch.float32, device=device) for _ in range(2)],
+                      "d_grad": [torch.empty(C, 3, dtype=torch.float32, device=device) for _ in range(2)]}
+                self._pipe_state = st
+            s_in, s_out = st["s_in"], st["s_out"]
+            val_h = torch.empty(n, dtype=torch.float32, pin_memory=True)
+            grad_h = torch.empty(n, 3, dtype=torch.float32, pin_memory=True)
+            L = nat.lib()
+            s_in.wait_stream(cur)
+            s_out.wait_stream(cur)
+            ev_comp = [None, None]      # lookup finished reading d_in[b] / writing d_val[b]
+            ev_out = [None, None]       # copy-out finished reading d_val[b]
+            for i, lo in enumerate(range(0, n, C)):
+                hi = min(lo + C, n)
+                m = hi - lo
+                b = i & 1
+                with torch.cuda.stream(s_in):
+                    if ev_comp[b] is not None:
+                        s_in.wait_event(ev_comp[b])
+                    st["d_in"][b][:m].copy_(src[lo:hi], non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(s_in)
+                cur.wait_event(ev_in)
+                if ev_out[b] is not None:
+                    cur.wait_event(ev_out[b])
+                nat.check(L.pvb_grid_lookup(ctypes.byref(self._desc), nat.ptr(st["d_in"][b]), m,
+                                            nat.ptr(st["d_val"][b]), nat.ptr(st["d_grad"][b]), None, 0.0, None,
+                                            nat.stream_ptr(device)), "pvb_grid_lookup")
+                ev_comp[b] = torch.cuda.Event()
+                ev_comp[b].record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_comp[b])
+                    val_h[lo:hi].copy_(st["d_val"][b][:m], non_blocking=True)
+                    grad_h[lo:hi].copy_(st["d_grad"][b][:m], non_blocking=True)
+                    ev_out[b] = torch.cuda.Event()
+                    ev_out[b].record(s_out)
+            s_out.synchronize()
+            cur.wait_stream(s_in)
+        return val_h, grad_h
+
     def __call__(self, points_in_object_frame):
         lead = tuple(points_in_object_frame.shape[:-1])
         gt_outside_kernel = (self.out_of_bounds_strategy == OutOfBoundsStrategy.LOOKUP_GT_SDF
                              and not self._gt_in_kernel)
+        if (torch.is_tensor(points_in_object_frame) and points_in_object_frame.device.type == "cpu"
+                and torch.device(self.device).type == "cpu" and not gt_outside_kernel and not self.debug_check_sdf
+                and points_in_object_frame.numel() // 3 >= self.host_pipeline_min_points):
+            val, grad = self._host_pipeline(points_in_object_frame)
+            dtype = points_in_object_frame.dtype
+            if dtype != torch.float32:
+                val, grad = val.to(dtype), grad.to(dtype)
+            return val.reshape(lead), grad.reshape(*lead, 3)
         p, val, grad, _, index = self._lookup(points_in_object_frame, want_index=gt_outside_kernel or
                                               self.debug_check_sdf)
         if gt_outside_kernel:

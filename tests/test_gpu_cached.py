@@ -155,6 +155,15 @@ def test_cached_c2_full_size_properties(tmp_path):
     perm = torch.randperm(n, device="cuda")[:1_000_000]
     vp, gp = c(q[perm])
     assert torch.equal(vp, val[perm]) and torch.equal(gp, grad[perm])
+    # host path: pinned host tensor in, host tensors out through the chunked three-stream pipeline, bit-identical
+    ch = pv.CachedSDF("drill", 0.005, obj.bounding_box(padding=0.1), gt, device="cpu",
+                      cache_path=str(tmp_path / "c2.pkl"))
+    qh = q[:5_000_003].cpu().pin_memory()
+    vh, gh = ch(qh)
+    assert vh.device.type == "cpu" and vh.is_pinned()
+    assert torch.equal(vh, val[:5_000_003].cpu()) and torch.equal(gh, grad[:5_000_003].cpu())
+    vh2, gh2 = ch(qh[:1000].double())                       # small batch, other dtype: plain path
+    assert vh2.dtype == torch.float64 and torch.equal(vh2.float(), val[:1000].cpu())
     # batch dims
     vb, gb = c(q[:6000].view(2, 30, 100, 3))
     assert vb.shape == (2, 30, 100) and gb.shape == (2, 30, 100, 3)
