@@ -663,6 +663,9 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
 // the point.  Results are bit-identical to the point-major kernel (same transform / lookup arithmetic; pruning is
 // exact).  A block owns a tile of 32 configurations x 32 points; results are transposed through shared memory so
 // that global stores stay coalesced along the point axis.
+#ifndef PVB_CM_BESTFIRST
+#define PVB_CM_BESTFIRST 1
+#endif
 constexpr int kCmCfg = 32;
 constexpr int kCmWarps = 8;
 constexpr int kCmPts = 4;                         // points per thread
@@ -734,22 +737,9 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
         int bs[kCmPts];
 #pragma unroll
         for (int k = 0; k < kCmPts; ++k) { best[k] = PVB_INF; bg[k] = mk3(0.f, 0.f, 0.f); bs[k] = -1; }
-        for (int s = 0; s < n_sdf; ++s) {
+        // One sub-SDF visit for the points of this thread that still need it: transform, AABB bound, lookup.
+        auto visit = [&](int s, const bool (&need)[kCmPts]) {
             const pvb_sdf_desc &d = descs.d[s];
-            const float4 sp = sm.sph[lane][s];
-            bool need[kCmPts];
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < kCmPts; ++k) {
-                // stage 1: value >= |p - c_obj| - radius - margin (isometry); 0.9998 absorbs the 1e-5 non-rigidity
-                const float thr = best[k] + sp.w;
-                const float dx = p[k].x - sp.x, dy = p[k].y - sp.y, dz = p[k].z - sp.z;
-                const float d2 = dx * dx + dy * dy + dz * dz;
-                const bool pruned = bs[k] >= 0 && (thr < 0.f || d2 * 0.9998f > thr * thr);
-                need[k] = pon[k] && !pruned;
-                any |= need[k];
-            }
-            if (!any) continue;
             const float4 r0 = sm.xf[lane][3 * s], r1 = sm.xf[lane][3 * s + 1], r2 = sm.xf[lane][3 * s + 2];
             const bool prunable = d.kind == PVB_KIND_GRID && (d.flags & PVB_GRID_PRUNE_OK);
 #pragma unroll
@@ -769,10 +759,55 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
                 SdfOut o;
                 if (d.kind == PVB_KIND_GRID) o = grid_eval<false, true>(d, st, q, 0u, 0ull, nullptr);
                 else o = sphere_eval(d.radius, q);
+                // torch.argmin (sdf.py:421): smallest value, first index on ties, whatever the visiting order
                 if (bs[k] < 0 || o.val < best[k] || (o.val == best[k] && s < bs[k])) {
                     best[k] = o.val; bg[k] = o.grad; bs[k] = s;
                 }
             }
+        };
+        // pass 0 (no table access, no transform): the link whose bounding sphere is nearest goes first, so that the
+        // running min is already tight when the others are considered (PVB_CM_BESTFIRST)
+        int first[kCmPts];
+#pragma unroll
+        for (int k = 0; k < kCmPts; ++k) first[k] = -1;
+        if (PVB_CM_BESTFIRST && n_sdf > 1) {
+            float lbmin[kCmPts];
+#pragma unroll
+            for (int k = 0; k < kCmPts; ++k) { lbmin[k] = PVB_INF; first[k] = 0; }
+            for (int s = 0; s < n_sdf; ++s) {
+                const float4 sp = sm.sph[lane][s];
+                const float rad = sp.w < PVB_INF ? sp.w : 0.f;
+#pragma unroll
+                for (int k = 0; k < kCmPts; ++k) {
+                    const float dx = p[k].x - sp.x, dy = p[k].y - sp.y, dz = p[k].z - sp.z;
+                    // ordering key only (not a bound): squared centre distance minus squared radius
+                    const float key = dx * dx + dy * dy + dz * dz - rad * rad;
+                    if (key < lbmin[k]) { lbmin[k] = key; first[k] = s; }
+                }
+            }
+            for (int s = 0; s < n_sdf; ++s) {          // descriptor index stays warp-uniform
+                bool need[kCmPts];
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < kCmPts; ++k) { need[k] = pon[k] && first[k] == s; any |= need[k]; }
+                if (any) visit(s, need);
+            }
+        }
+        for (int s = 0; s < n_sdf; ++s) {
+            const float4 sp = sm.sph[lane][s];
+            bool need[kCmPts];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < kCmPts; ++k) {
+                // stage 1: value >= |p - c_obj| - radius - margin (isometry); 0.9998 absorbs the 1e-5 non-rigidity
+                const float thr = best[k] + sp.w;
+                const float dx = p[k].x - sp.x, dy = p[k].y - sp.y, dz = p[k].z - sp.z;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                const bool pruned = bs[k] >= 0 && (thr < 0.f || d2 * 0.9998f > thr * thr);
+                need[k] = pon[k] && !pruned && first[k] != s;
+                any |= need[k];
+            }
+            if (any) visit(s, need);
         }
         // rotate the winning gradients back (g @ M[:3,:3]) and park the results for the transposed store
 #pragma unroll
