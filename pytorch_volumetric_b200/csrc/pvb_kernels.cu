@@ -664,7 +664,9 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
 // exact).  A block owns a tile of 32 configurations x 32 points; results are transposed through shared memory so
 // that global stores stay coalesced along the point axis.
 #ifndef PVB_CM_BESTFIRST
-#define PVB_CM_BESTFIRST 1
+// 1: visit the link with the nearest bounding sphere first.  Measured (C4 / README shape): 1.26 / 0.224 ms against
+// 1.05 / 0.182 ms for plain index order -- like PVB_COMP_BESTFIRST, the extra pass costs more than the lookups it saves.
+#define PVB_CM_BESTFIRST 0
 #endif
 constexpr int kCmCfg = 32;
 constexpr int kCmWarps = 8;
