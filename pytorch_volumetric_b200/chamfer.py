@@ -58,6 +58,8 @@ def batch_chamfer_dist(world_to_object: torch.tensor, model_points_world_frame_e
 
     B = world_to_object.shape[0]
     out_dtype, out_device = world_to_object.dtype, world_to_object.device
+    if B == 0 or model_points_world_frame_eval.shape[0] == 0:       # mean over nothing: NaN, as torch's .mean()
+        return torch.full((B,), float("nan"), dtype=out_dtype, device=out_device)
     with torch.cuda.device(dev):
         W = world_to_object.detach().to(device=dev, dtype=torch.float32).contiguous()
         p = nat.as_f32_points(model_points_world_frame_eval, dev)
