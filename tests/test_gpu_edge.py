@@ -95,7 +95,7 @@ def test_composed_single_sdf_and_nested(probe_cached):
     local = q @ m[0, :3, :3].T + m[0, :3, 3]
     v_ref, g_ref = c(local)
     # torch's matmul and the kernel's FMA chain round the transformed point differently: a few voxel keys flip
-    same = v == v_ref
+    same = (v - v_ref).abs() < 1e-6
     assert (~same).float().mean() < 2e-3
     assert ((g - g_ref @ m[0, :3, :3]).abs().max(-1).values[same]).max() < 1e-6
     inner = pv.ComposedSDF([c, pv.SphereSDF(0.01)], pv.Transform3d(matrix=m[:2]))
