@@ -157,15 +157,35 @@ def compute_device(device=None):
 
 
 def stream_ptr(device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return torch.cuda.current_stream(device).cuda_stream      # int; ctypes converts it for the void* parameter
 
 
 def ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    return t.data_ptr() if t is not None else None              # int -> void* (argtypes are declared)
+
+
+class on_device:
+    """`with torch.cuda.device(d)` only when d is not already current (the guard costs ~8 us per call)."""
+    __slots__ = ("guard",)
+
+    def __init__(self, device):
+        self.guard = None if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
 
 
 def as_f32_points(points, device):
     """[..., 3] tensor/ndarray -> contiguous fp32 (M,3) on `device` (H2D copy if the input is on the host)."""
+    if (torch.is_tensor(points) and points.dtype == torch.float32 and points.device == device
+            and points.is_contiguous() and points.shape[-1] == 3):
+        return points.detach().view(-1, 3)          # the common case: nothing to convert
     if not torch.is_tensor(points):
         points = torch.as_tensor(np.asarray(points))
     p = points.detach().reshape(-1, points.shape[-1])
@@ -186,8 +206,9 @@ def deliver(t, device, dtype=None):
     the host-buffer path run at PCIe speed instead of pageable-copy speed."""
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
-    device = torch.device(device)
-    if t.device == device:
+    if not isinstance(device, torch.device):
+        device = torch.device(device)
+    if t.device == device or (device.type == "cuda" and device.index is None and t.device.type == "cuda"):
         return t
     if device.type == "cpu" and t.device.type == "cuda":
         out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)

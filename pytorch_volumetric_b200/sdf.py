@@ -713,7 +713,7 @@ class CachedSDF(ObjectFrameSDF):
 
     def _lookup(self, points, want_val=True, want_outside=False, surface_level=0., want_index=False):
         device = self._cdev
-        with torch.cuda.device(device):
+        with nat.on_device(device):
             p = nat.as_f32_points(points, device)
             n = p.shape[0]
             val = torch.empty(n, dtype=torch.float32, device=device) if want_val else None
