@@ -77,14 +77,8 @@ __device__ __forceinline__ float box_d2(float lx, float ly, float lz, float hx, 
     return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
 }
 
-// Nearest-first BVH4 descent.  `init_d2` is an initial search radius (squared); candidates farther than that are
-// never reported (face stays -1).
-//
-// Leaves are stack entries like inner nodes: one loop iteration either expands a node or tests the (<= 4) triangles
-// of one leaf.  The first version tested leaves inline, child slot by child slot, and its triangle code ran with 7-11
-// of 32 lanes active (profiles/README.md); with leaves on the stack the lanes of a warp that are in "leaf mode" run
-// the triangle loop together, and leaves are visited in distance order across nodes, so fewer of them survive the
-// running bound.
+// Nearest-first BVH4 descent.  `init_d2` is an initial search radius (squared);
+// candidates farther than that are never reported (face stays -1).
 __device__ __forceinline__ Closest bvh_closest(const float4 *__restrict__ gnodes, const NodeStage &st,
                                                const float4 *__restrict__ tris, f3 p, float init_d2) {
     Closest best;
@@ -99,28 +93,9 @@ __device__ __forceinline__ Closest bvh_closest(const float4 *__restrict__ gnodes
     constexpr float kSlack = 0.99999f;
     while (sp > 0) {
         --sp;
-        const int ref = stack_n[sp];
+        const int ni = stack_n[sp];
         if (stack_d[sp] * kSlack > best.d2) continue;
-        if (ref < 0) {                                   // leaf: ~ref = (first_triangle << 2) | (count - 1)
-            const unsigned code = (unsigned)~ref;
-            const int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
-            for (int t = first; t < first + cnt; ++t) {
-                const float4 v0 = __ldg(tris + 3 * (size_t)t);
-                const float4 v1 = __ldg(tris + 3 * (size_t)t + 1);
-                const float4 v2 = __ldg(tris + 3 * (size_t)t + 2);
-                const f3 q = closest_on_triangle(p, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z),
-                                                 mk3(v2.x, v2.y, v2.z));
-                const f3 g = q - p;
-                const float dd = dot(g, g);
-                const int face = __float_as_int(v0.w);
-                // ties -> lowest original face index (the oracle's brute-force rule)
-                if (dd < best.d2 || (dd == best.d2 && (best.face < 0 || face < best.face))) {
-                    best.d2 = dd; best.q = q; best.face = face;
-                }
-            }
-            continue;
-        }
-        const float4 *n = node_ptr(gnodes, st, ref);
+        const float4 *n = node_ptr(gnodes, st, ni);
         const float4 lox = n[0], loy = n[1], loz = n[2], hix = n[3], hiy = n[4], hiz = n[5];
         const int4 ch = *reinterpret_cast<const int4 *>(n + 6);
         float d[4];
@@ -138,10 +113,32 @@ __device__ __forceinline__ Closest bvh_closest(const float4 *__restrict__ gnodes
                        const int tc = c[i]; c[i] = c[j]; c[j] = tc; }
         PVB_CSWAP(0, 1) PVB_CSWAP(2, 3) PVB_CSWAP(0, 2) PVB_CSWAP(1, 3) PVB_CSWAP(1, 2)
 #undef PVB_CSWAP
-        // farthest pushed first, so the nearest child (leaf or node) is popped next
+        // leaves first (nearest first) so that the bound tightens before pushing
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c[k] < 0 && c[k] != INT32_MIN && d[k] * kSlack <= best.d2) {
+                const unsigned code = (unsigned)~c[k];
+                const int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
+                for (int t = first; t < first + cnt; ++t) {
+                    const float4 v0 = __ldg(tris + 3 * (size_t)t);
+                    const float4 v1 = __ldg(tris + 3 * (size_t)t + 1);
+                    const float4 v2 = __ldg(tris + 3 * (size_t)t + 2);
+                    const f3 q = closest_on_triangle(p, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z),
+                                                     mk3(v2.x, v2.y, v2.z));
+                    const f3 g = q - p;
+                    const float dd = dot(g, g);
+                    const int face = __float_as_int(v0.w);
+                    // ties -> lowest original face index (the oracle's brute-force rule)
+                    if (dd < best.d2 || (dd == best.d2 && (best.face < 0 || face < best.face))) {
+                        best.d2 = dd; best.q = q; best.face = face;
+                    }
+                }
+            }
+        }
+        // inner children, farthest pushed first
 #pragma unroll
         for (int k = 3; k >= 0; --k) {
-            if (c[k] != INT32_MIN && d[k] * kSlack <= best.d2 && sp < kStack) {
+            if (c[k] >= 0 && d[k] * kSlack <= best.d2 && sp < kStack) {
                 stack_n[sp] = c[k]; stack_d[sp] = d[k]; ++sp;
             }
         }
