@@ -83,17 +83,26 @@ def batch_chamfer_dist(world_to_object: torch.tensor, model_points_world_frame_e
 def pairwise_distance_chamfer(A_link_to_world_tfs, B_world_to_link_tfs=None,
                               obj_factory: ObjectFactory = None, obj_sdf: ObjectFrameSDF = None,
                               model_points_eval: torch.tensor = None, vis=None, scale=1000):
-    """B x P matrix of chamfer distances between every pairing T_inv[b] @ T[p] (chamfer.py:20-59)."""
-    T = matrix_of(A_link_to_world_tfs)
+    """Chamfer distance of every pairing of two pose sets (reference chamfer.py:20-59).
+
+    Entry [b, p] scores the composite transform B[p] @ A[b] (identity when the two poses agree); B defaults to the
+    inverses of A.  All B*P composites go through one `batch_chamfer_dist` launch.
+    """
+    link_to_world = matrix_of(A_link_to_world_tfs)
     if model_points_eval is None:
         model_points_eval, _, _ = sample_mesh_points(obj_factory, num_points=500, name=obj_factory.name,
-                                                     device=T.device)
-    T_inv = invert_rigid(T) if B_world_to_link_tfs is None else matrix_of(B_world_to_link_tfs)
-    Iapprox = torch.einsum("bij,pjk->bpik", T_inv, T)
-    B, P = len(T), len(T_inv)
-    errors = batch_chamfer_dist(Iapprox.reshape(B * P, 4, 4), model_points_eval, obj_factory=obj_factory,
+                                                     device=link_to_world.device)
+    world_to_link = invert_rigid(link_to_world) if B_world_to_link_tfs is None else matrix_of(B_world_to_link_tfs)
+    return _pairwise_chamfer(world_to_link, link_to_world, model_points_eval, obj_factory, obj_sdf, scale, vis)
+
+
+def _pairwise_chamfer(left, right, points, obj_factory, obj_sdf, scale, vis=None):
+    """errors[i, j] = chamfer(left[i] @ right[j]) as an (len(left), len(right)) matrix."""
+    composite = torch.einsum("bij,pjk->bpik", left, right)
+    n_left, n_right = composite.shape[:2]
+    errors = batch_chamfer_dist(composite.reshape(n_left * n_right, 4, 4), points, obj_factory=obj_factory,
                                 obj_sdf=obj_sdf, viewing_delay=0, vis=vis, scale=scale)
-    return errors.view(B, P)
+    return errors.view(n_left, n_right)
 
 
 class PlausibleDiversityReturn(NamedTuple):
@@ -104,44 +113,38 @@ class PlausibleDiversityReturn(NamedTuple):
 
 
 class PlausibleDiversity:
-    """Plausibility and coverage of an estimated transform set against a plausible transform set, in squared
-    (scaled) coordinate units (chamfer.py:130-195)."""
+    """Set divergence between estimated and plausible pose sets (reference chamfer.py:130-195), in squared scaled
+    units: plausibility = mean over estimates of the best match among the plausible poses, coverage = mean over
+    plausible poses of the best match among the estimates."""
 
     def __init__(self, obj_factory: ObjectFactory, model_points_eval: torch.tensor = None, num_model_points_eval=500,
                  obj_sdf: ObjectFrameSDF = None):
         self.obj_factory = obj_factory
         self.obj_sdf = obj_sdf
         if model_points_eval is None:
-            model_points_eval, _, _ = sample_mesh_points(obj_factory, num_points=num_model_points_eval,
-                                                         name=obj_factory.name)
+            model_points_eval = sample_mesh_points(obj_factory, num_points=num_model_points_eval,
+                                                   name=obj_factory.name)[0]
         self.model_points_eval = model_points_eval
 
-    def __call__(self, T_est_inv, T_p, bidirectional=False, scale=1000.):
-        errors = self.compute_tf_pairwise_error_per_batch(T_est_inv, T_p, scale=scale)
-        ret = self.do_evaluate_plausible_diversity_on_pairwise_chamfer_dist(errors)
-        if bidirectional:
-            errors_rev = self.compute_tf_pairwise_error_per_batch(T_p, T_est_inv, scale=scale)
-            ret2 = self.do_evaluate_plausible_diversity_on_pairwise_chamfer_dist(errors_rev)
-            ret = PlausibleDiversityReturn(
-                plausibility=(ret.plausibility + ret2.coverage) / 2,
-                coverage=(ret.coverage + ret2.plausibility) / 2,
-                most_plausible_per_estimated=ret.most_plausible_per_estimated,
-                most_covered_per_plausible=ret.most_covered_per_plausible,
-            )
-        return ret
-
     def compute_tf_pairwise_error_per_batch(self, T_est_inv, T_p, scale=1000.):
-        Iapprox = torch.einsum("bij,pjk->bpik", T_est_inv, T_p)
-        B, P = Iapprox.shape[:2]
-        self.model_points_eval = self.model_points_eval.to(device=Iapprox.device, dtype=Iapprox.dtype)
-        errors = batch_chamfer_dist(Iapprox.reshape(B * P, 4, 4), self.model_points_eval, self.obj_factory,
-                                    obj_sdf=self.obj_sdf, viewing_delay=0, vis=None, scale=scale)
-        return errors.view(B, P)
+        self.model_points_eval = self.model_points_eval.to(device=T_est_inv.device, dtype=T_est_inv.dtype)
+        return _pairwise_chamfer(T_est_inv, T_p, self.model_points_eval, self.obj_factory, self.obj_sdf, scale)
 
     @staticmethod
     def do_evaluate_plausible_diversity_on_pairwise_chamfer_dist(errors_per_batch):
-        B, P = errors_per_batch.shape
-        best_per_sampled = errors_per_batch.min(dim=1)
-        best_per_plausible = errors_per_batch.min(dim=0)
-        return PlausibleDiversityReturn(best_per_sampled.values.sum() / B, best_per_plausible.values.sum() / P,
-                                        best_per_sampled, best_per_plausible)
+        per_estimate = errors_per_batch.min(dim=1)
+        per_plausible = errors_per_batch.min(dim=0)
+        return PlausibleDiversityReturn(per_estimate.values.mean(), per_plausible.values.mean(),
+                                        per_estimate, per_plausible)
+
+    def __call__(self, T_est_inv, T_p, bidirectional=False, scale=1000.):
+        score = self.do_evaluate_plausible_diversity_on_pairwise_chamfer_dist
+        forward = score(self.compute_tf_pairwise_error_per_batch(T_est_inv, T_p, scale=scale))
+        if not bidirectional:
+            return forward
+        # with the roles of the two sets swapped, plausibility and coverage trade places
+        backward = score(self.compute_tf_pairwise_error_per_batch(T_p, T_est_inv, scale=scale))
+        return PlausibleDiversityReturn(plausibility=(forward.plausibility + backward.coverage) / 2,
+                                        coverage=(forward.coverage + backward.plausibility) / 2,
+                                        most_plausible_per_estimated=forward.most_plausible_per_estimated,
+                                        most_covered_per_plausible=forward.most_covered_per_plausible)

@@ -1,9 +1,9 @@
-"""RobotSDF: per-link SDFs posed by batched forward kinematics, min over links.
+"""RobotSDF: one SDF per link mesh, posed by batched forward kinematics, min over links in one fused kernel.
 
-Mirrors /root/reference/src/pytorch_volumetric/model_to_sdf.py (RobotSDF :12-125,
-cache_link_sdf_factory :128-133, aabb_to_ordered_end_points :136-171).  `chain` is duck-typed on the
-pytorch_kinematics Chain surface (see kinematics.py); the query itself is one fused kernel
-(pvb_composed_query) per call.
+API mirror of /root/reference/src/pytorch_volumetric/model_to_sdf.py (RobotSDF :12-125,
+cache_link_sdf_factory :128-133, aabb_to_ordered_end_points :136-171): same constructor arguments, attributes,
+output shapes and state semantics.  `chain` is duck-typed on the pytorch_kinematics Chain surface listed in
+kinematics.py; every query is a single pvb_composed_query launch.
 """
 import logging
 import typing
@@ -12,115 +12,120 @@ import numpy as np
 import torch
 
 from . import sdf
-from .transforms import Transform3d, matrix_of, invert_rigid
+from .transforms import Transform3d, invert_rigid, matrix_of
 
 logger = logging.getLogger(__file__)
 
 
+def _mesh_visuals(chain, frame_names):
+    """(link name, visual) for every mesh visual along the chain, in frame order; other geometry types are
+    reported and skipped, like the reference does (model_to_sdf.py:41-56)."""
+    for fname in frame_names:
+        link = chain.find_frame(fname).link
+        for vis in link.visuals:
+            if vis.geom_type == "mesh":
+                yield link.name, vis
+            else:
+                logger.warning("Cannot handle non-mesh link visual type %s for %s", vis, link.name)
+
+
 class RobotSDF(sdf.ObjectFrameSDF):
-    """SDF of a robot model described by a kinematic chain, conditioned on a joint configuration
-    (optionally a batch of configurations) that must be set before querying."""
+    """SDF of an articulated robot in its base frame.
+
+    The joint configuration -- a single vector or an arbitrarily batched set of them -- is state: it is installed
+    with `set_joint_configuration` and determines both the values and the leading shape of what `__call__` returns.
+    """
 
     def __init__(self, chain, default_joint_config=None, path_prefix='',
                  link_sdf_cls: typing.Callable[[sdf.ObjectFactory], sdf.ObjectFrameSDF] = sdf.MeshSDF):
         """
-        :param chain: robot description; each link visual should be a mesh - non-mesh geometries are ignored
-        :param default_joint_config: values for each joint by default; None results in all zeros
-        :param path_prefix: prefix for the (relative) mesh paths referenced inside the robot description
-        :param link_sdf_cls: factory of each link's SDF from its ObjectFactory
+        :param chain: kinematic description; only mesh visuals become SDFs
+        :param default_joint_config: joint values installed at construction (zeros when None)
+        :param path_prefix: directory the relative mesh paths of the description are resolved against
+        :param link_sdf_cls: callable turning a link's ObjectFactory into its ObjectFrameSDF
         """
         self.chain = chain
-        self.dtype = self.chain.dtype
-        self.device = self.chain.device
+        self.dtype, self.device = chain.dtype, chain.device
         self.q = None
-        self.object_to_link_frames = None
-        self.joint_names = self.chain.get_joint_parameter_names()
-        self.frame_names = self.chain.get_frame_names(exclude_fixed=False)
-        self.sdf: typing.Optional[sdf.ComposedSDF] = None
-        self.sdf_to_link_name = []
         self.configuration_batch = None
+        self.object_to_link_frames = None
+        self.joint_names = chain.get_joint_parameter_names()
+        self.frame_names = chain.get_frame_names(exclude_fixed=False)
 
-        sdfs = []
-        offsets = []
-        for frame_name in self.frame_names:
-            frame = self.chain.find_frame(frame_name)
-            for link_vis in frame.link.visuals:
-                if link_vis.geom_type == "mesh":
-                    logger.info(f"{frame.link.name} offset {link_vis.offset}")
-                    link_obj = sdf.MeshObjectFactory(link_vis.geom_param[0],
-                                                     scale=link_vis.geom_param[1],
-                                                     path_prefix=path_prefix)
-                    link_sdf = link_sdf_cls(link_obj)
-                    self.sdf_to_link_name.append(frame.link.name)
-                    sdfs.append(link_sdf)
-                    offsets.append(link_vis.offset)
-                else:
-                    logger.warning(f"Cannot handle non-mesh link visual type {link_vis} for {frame.link.name}")
-
-        off = torch.cat([matrix_of(o) for o in offsets], dim=0)
-        self.offset_transforms = Transform3d(matrix=off.to(device=self.device, dtype=self.dtype))
-        self.sdf = sdf.ComposedSDF(sdfs, self.object_to_link_frames)
+        visuals = list(_mesh_visuals(chain, self.frame_names))
+        self.sdf_to_link_name = [name for name, _ in visuals]
+        link_sdfs = []
+        for name, vis in visuals:
+            mesh_file, mesh_scale = vis.geom_param[0], vis.geom_param[1]
+            logger.info("%s offset %s", name, vis.offset)
+            link_sdfs.append(link_sdf_cls(sdf.MeshObjectFactory(mesh_file, scale=mesh_scale, path_prefix=path_prefix)))
+        # visual origin of every mesh inside its link frame, stacked link-major
+        self.offset_transforms = Transform3d(
+            matrix=torch.cat([matrix_of(vis.offset) for _, vis in visuals]).to(device=self.device, dtype=self.dtype))
+        self.sdf: typing.Optional[sdf.ComposedSDF] = sdf.ComposedSDF(link_sdfs, None)
         self.set_joint_configuration(default_joint_config)
+
+    # ------------------------------------------------------------------ state
+    def set_joint_configuration(self, joint_config=None):
+        """Install joint values of shape [*A, n_joints]; A (possibly empty) becomes the leading shape of results."""
+        n_joints = len(self.joint_names)
+        if joint_config is None:
+            joint_config = torch.zeros(n_joints, device=self.device, dtype=self.dtype)
+        batched = joint_config.dim() > 1
+        self.configuration_batch = tuple(joint_config.shape[:-1]) if batched else None
+        if self.configuration_batch is not None:
+            self.configuration_batch = torch.Size(self.configuration_batch)
+        flat_q = joint_config.reshape(-1, n_joints) if batched else joint_config
+        self.q = flat_q
+        poses = self.chain.forward_kinematics(flat_q, end_only=False)
+        world_from_link = torch.stack([matrix_of(poses[name]) for name in self.sdf_to_link_name])   # (S, |A|, 4, 4)
+        n_links, n_cfg = world_from_link.shape[:2]
+        mesh_from_link = invert_rigid(matrix_of(self.offset_transforms)).to(world_from_link)        # (S, 4, 4)
+        # base frame -> mesh frame of each link: (FK @ visual_offset)^-1, link-major like the reference's stack
+        mesh_from_world = mesh_from_link[:, None] @ invert_rigid(world_from_link)
+        self.object_to_link_frames = Transform3d(matrix=mesh_from_world.reshape(n_links * n_cfg, 4, 4))
+        if self.sdf is not None:
+            self.sdf.set_transforms(self.object_to_link_frames, batch_dim=self.configuration_batch)
+
+    # ---------------------------------------------------------------- queries
+    def __call__(self, points_in_object_frame):
+        """points [*B, N, 3] in the robot frame -> (values [*A, *B, N], gradients [*A, *B, N, 3])."""
+        return self.sdf(points_in_object_frame)
 
     def surface_bounding_box(self, **kwargs):
         return self.sdf.surface_bounding_box(**kwargs)
 
     def link_bounding_boxes(self):
-        """[A x] [B x] 8 x 3 corner points of each link's box in the robot frame under the current configuration."""
-        tfs = Transform3d(matrix=invert_rigid(matrix_of(self.sdf.obj_frame_to_link_frame)))
-        bbs = []
-        for i in range(len(self.sdf.sdfs)):
-            link_sdf = self.sdf.sdfs[i]
-            bb = aabb_to_ordered_end_points(np.asarray(link_sdf.surface_bounding_box(padding=0)))
-            bb = tfs.transform_points(torch.tensor(bb, device=tfs.device, dtype=tfs.dtype))[
-                self.sdf.ith_transform_slice(i)]
-            bbs.append(bb)
-        return torch.stack(bbs).squeeze()
+        """Corner points (8 x 3, robot frame) of every link's box under the installed configuration(s)."""
+        world_from_mesh = Transform3d(matrix=invert_rigid(matrix_of(self.sdf.obj_frame_to_link_frame)))
+        per_link = []
+        for i, link_sdf in enumerate(self.sdf.sdfs):
+            corners = aabb_to_ordered_end_points(np.asarray(link_sdf.surface_bounding_box(padding=0)))
+            corners = torch.tensor(corners, device=world_from_mesh.device, dtype=world_from_mesh.dtype)
+            per_link.append(world_from_mesh.transform_points(corners)[self.sdf.ith_transform_slice(i)])
+        return torch.stack(per_link).squeeze()
 
-    def set_joint_configuration(self, joint_config=None):
-        """
-        :param joint_config: [A x] M optionally arbitrarily batched joint configurations (M joints)
-        """
-        M = len(self.joint_names)
-        if joint_config is None:
-            joint_config = torch.zeros(M, device=self.device, dtype=self.dtype)
-        if len(joint_config.shape) > 1:
-            self.configuration_batch = joint_config.shape[:-1]
-            joint_config = joint_config.reshape(-1, M)
-        else:
-            self.configuration_batch = None
-        self.q = joint_config
-        tf = self.chain.forward_kinematics(joint_config, end_only=False)
-        # link-major stack of (|A|,4,4) link poses (model_to_sdf.py:100-102, 112)
-        link_pose = torch.stack([matrix_of(tf[name]) for name in self.sdf_to_link_name])
-        S, A = link_pose.shape[0], link_pose.shape[1]
-        offset_inv = invert_rigid(matrix_of(self.offset_transforms)).to(link_pose)
-        # object -> link = offset^-1 @ FK^-1 = (FK @ offset)^-1   (model_to_sdf.py:104-113)
-        obj_to_link = offset_inv[:, None] @ invert_rigid(link_pose)
-        self.object_to_link_frames = Transform3d(matrix=obj_to_link.reshape(S * A, 4, 4))
-        if self.sdf is not None:
-            self.sdf.set_transforms(self.object_to_link_frames, batch_dim=self.configuration_batch)
 
-    def __call__(self, points_in_object_frame):
-        """
-        :param points_in_object_frame: [B x] N x 3 points in the robot frame
-        :return: [A x] [B x] N SDF value and [A x] [B x] N x 3 SDF gradient (A = configuration batch dims)
-        """
-        return self.sdf(points_in_object_frame)
+class _CachedLinkFactory:
+    """Picklable callable behind `cache_link_sdf_factory`."""
+
+    def __init__(self, resolution, padding, kwargs):
+        self.resolution, self.padding, self.kwargs = resolution, padding, kwargs
+
+    def __call__(self, obj_factory: sdf.ObjectFactory):
+        box = obj_factory.bounding_box(padding=self.padding)
+        return sdf.CachedSDF(obj_factory.name, self.resolution, box, sdf.MeshSDF(obj_factory), **self.kwargs)
 
 
 def cache_link_sdf_factory(resolution=0.01, padding=0.1, **kwargs):
-    def create_sdf(obj_factory: sdf.ObjectFactory):
-        gt_sdf = sdf.MeshSDF(obj_factory)
-        return sdf.CachedSDF(obj_factory.name, resolution, obj_factory.bounding_box(padding=padding), gt_sdf, **kwargs)
-
-    return create_sdf
+    """`link_sdf_cls` that wraps every link mesh in a CachedSDF over its padded bounding box."""
+    return _CachedLinkFactory(resolution, padding, kwargs)
 
 
 def aabb_to_ordered_end_points(aabb, arrange_in_sequential_order=False):
+    """8 corners of a (3,2) box, or (sequential order) a 16-point closed walk over its edges for line drawing."""
     lo, hi = aabb[:, 0], aabb[:, 1]
     if arrange_in_sequential_order:
-        # a closed walk over the 12 edges (line-strip drawing order)
         code = ["000", "100", "110", "010", "000", "001", "101", "100", "101", "111", "110", "111", "011", "010",
                 "011", "001"]
     else:
