@@ -280,9 +280,11 @@ class C4(Workload):
     name = "c4"
     kernel = "composed_query_kernel<false>"
 
-    def __init__(self, rank, world=1, n_cfg=200, n_pts=100_000, cache_dir=None):
+    def __init__(self, rank, world=1, n_cfg=200, n_pts=100_000, cache_dir=None, gather=False):
         import pytorch_volumetric_b200 as pv
         from pytorch_volumetric_b200 import distributed as pd
+        self.gather = gather and world > 1
+        self.pd = pd
         d = os.path.join(cache_dir or tempfile.gettempdir(), f"pvb_bench_arm_{rank}")
         urdf, end = workloads.write_arm(d)
         chain = pv.build_serial_chain_from_urdf(open(urdf).read(), end).to(device="cuda")
@@ -306,9 +308,13 @@ class C4(Workload):
         self.desc = {"workload": f"C4 RobotSDF synthetic 7-DOF arm (8 links, CachedSDF res=0.02 pad=1.0, "
                                  f"{n_vox} voxels = {16 * n_vox / 1e6:.0f} MB tables) x {n_cfg} configurations x "
                                  f"{n_pts} points, configurations sharded over ranks",
-                     "configs_this_rank": self.end - self.begin, "l2_policy": "output 320 MB/step > L2"}
+                     "configs_this_rank": self.end - self.begin, "l2_policy": "output 320 MB/step > L2",
+                     "result_reassembly": "all-gather of the per-rank slabs (NCCL)" if self.gather else
+                     "none: every rank keeps its configuration slab"}
 
     def step(self, i):
+        if self.gather:      # every rank ends up with the full (200, M) result: one NCCL all-gather per tensor
+            return self.pd.sharded_robot_query(self.robot, self.dev[i % 3], gather=True)
         return self.robot.sdf.query(self.dev[i % 3], cfg_begin=self.begin, cfg_count=self.end - self.begin)
 
     def step_host(self, i):
@@ -408,6 +414,8 @@ def make_workload(name, rank, world):
         return Mesh10k(rank, n_lon=250, n_lat=101)
     if name == "c4":
         return C4(rank, world)
+    if name == "c4gather":
+        return C4(rank, world, gather=True)
     if name == "c4readme":
         return C4(rank, world, n_cfg=200, n_pts=15251)
     if name == "c5":
