@@ -1193,7 +1193,11 @@ extern "C" int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int3
     const long long n_vec = vec ? n_pts : 0;
     int rc = PVB_OK;
     static const int cfg_major = [] { const char *e = getenv("PVB_COMP_CFGMAJOR"); return e ? atoi(e) : 1; }();
-    if (cfg_major && !needs_mesh && n_sdf <= kCmMaxS && cfg_count >= 16) {
+    // lanes = configurations: only worthwhile when the 32-wide configuration tiles are well filled (25 configurations
+    // per rank on 8 GPUs would idle 22 % of the lanes; measured 0.176 ms against 0.111 ms point-major)
+    const int cm_tiles = (cfg_count + kCmCfg - 1) / kCmCfg;
+    const bool cm_filled = cfg_count >= 16 && (double)cfg_count >= 0.85 * (double)(cm_tiles * kCmCfg);
+    if (cfg_major && !needs_mesh && n_sdf <= kCmMaxS && cm_filled) {
         static const bool smem_ok = cudaFuncSetAttribute(composed_cfgmajor_kernel,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)sizeof(CmSmem)) == cudaSuccess;
