@@ -210,8 +210,11 @@ static size_t sort_workspace_bytes(long long n) {
 
 // ================================================================ mesh query
 constexpr int kMeshThreads = 256;
+#ifndef PVB_MESH_MINB
+#define PVB_MESH_MINB 1
+#endif
 
-__global__ void __launch_bounds__(kMeshThreads)
+__global__ void __launch_bounds__(kMeshThreads, PVB_MESH_MINB)
 mesh_query_kernel(const pvb_sdf_desc m, const float *__restrict__ pts, long long n,
                   const uint32_t *__restrict__ perm, int run, uint32_t mode, int n_stage_max, float *__restrict__ out_dist, float *__restrict__ out_grad, float *__restrict__ out_closest,
                   int *__restrict__ out_face, float *__restrict__ out_normal) {
@@ -969,7 +972,11 @@ constexpr int kStageNodesMax = 1536;   // 192 KB
 static int stage_nodes_for(int n_nodes) {
     static int max_nodes = -1;
     if (max_nodes < 0) {
-        max_nodes = 448;   // 56 KB: leaves most of the 228 KB carve-out to L1 for the deeper nodes and the stacks
+        // Measured (profiles/README.md, 1e7 queries on the 10k-triangle mesh / C5 chamfer): 0 -> 9.1 / 10.2 ms,
+        // 128 -> 9.4 ms, 448 -> 10.0 / 14.6 ms, 1024 -> 16.7 ms, 1536 -> 18.1 / 19.3 ms.  Shared memory taken from
+        // the unified 228 KB array is L1 taken away from the triangles, the deeper nodes and the traversal stacks,
+        // and the top of the tree is an L1 hit anyway; the bulk-copy staging path is kept (PVB_STAGE_NODES) but off.
+        max_nodes = 0;
         if (const char *e = getenv("PVB_STAGE_NODES")) {
             const int v = atoi(e);
             if (v >= 0 && v <= kStageNodesMax) max_nodes = v;
