@@ -463,6 +463,9 @@ constexpr int kCompSmemXf = 64;
 #ifndef PVB_COMP_MINB
 #define PVB_COMP_MINB 4
 #endif
+#ifndef PVB_COMPMESH_MINB
+#define PVB_COMPMESH_MINB 4   // C3 (16 drills): 16.4 / 14.6 / 13.1 ms at 1 / 3 / 4 CTAs per SM
+#endif
 #ifndef PVB_COMP_BESTFIRST
 // 1: evaluate the sub-SDF with the smallest AABB lower bound first (an extra pass over the transforms).  Measured
 // on C4 (profiles/README.md): fewer table gathers but 1.8x slower -- the kernel is instruction-issue bound, the
@@ -476,7 +479,7 @@ struct DescPack {
 };
 
 template <bool kMesh, int PTS, int MAXS>
-__global__ void __launch_bounds__(kCompThreads, (PTS > 1 ? PVB_COMP_MINB : 1))
+__global__ void __launch_bounds__(kCompThreads, (kMesh ? PVB_COMPMESH_MINB : (PTS > 1 ? PVB_COMP_MINB : 1)))
 composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, const float *__restrict__ xforms,
                       int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, long long first_pt,
                       long long n_pts, uint32_t mesh_mode, float *__restrict__ out_val, float *__restrict__ out_grad,
