@@ -108,6 +108,7 @@ class ObjectFactory(abc.ABC):
         self._bvh_host = None      # (nodes uint8[n,128], tris float32[F,12], depth)
         self._dev = {}             # device -> dict of device buffers
         self._closed = None
+        self._aabb = None
         self.precompute_sdf()
 
     def __reduce__(self):
@@ -132,9 +133,9 @@ class ObjectFactory(abc.ABC):
         return self.get_mesh_resource_filename()
 
     def bounding_box(self, padding=0., padding_ratio=0):
-        lo = self._mesh.vertices.min(axis=0)
-        hi = self._mesh.vertices.max(axis=0)
-        ranges = np.stack([lo, hi], axis=1)
+        if self._aabb is None:      # the vertices never change after construction
+            self._aabb = (self._mesh.vertices.min(axis=0), self._mesh.vertices.max(axis=0))
+        ranges = np.stack(self._aabb, axis=1)
         extents = ranges[:, 1] - ranges[:, 0]
         ranges[:, 0] -= padding + padding_ratio * extents
         ranges[:, 1] += padding + padding_ratio * extents
