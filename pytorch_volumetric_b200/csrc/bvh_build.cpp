@@ -47,6 +47,7 @@ struct Builder {
     std::vector<float> cent;   // 3 per triangle
     std::vector<int32_t> order;
     std::vector<BinNode> nodes;
+    bool force_median = false;   // balanced fallback when the SAH tree would be too deep for the traversal stack
 
     int build(int start, int count, int depth, int &max_depth) {
         const int id = (int)nodes.size();
@@ -66,7 +67,7 @@ struct Builder {
         // binned SAH over the three axes
         int best_axis = -1, best_bin = -1;
         float best_cost = INFINITY;
-        for (int ax = 0; ax < 3; ++ax) {
+        for (int ax = 0; ax < 3 && !force_median; ++ax) {
             const float ext = cbox.hi[ax] - cbox.lo[ax];
             if (!(ext > 0.f)) continue;
             Box bb[kBins]; int bc[kBins];
@@ -126,51 +127,9 @@ struct Builder {
 
 }  // namespace
 
-extern "C" int64_t pvb_bvh_max_nodes(int64_t n_faces) {
-    // every wide node has >= 2 children, leaves hold >= 1 triangle
-    return n_faces < 1 ? 1 : n_faces;
-}
+// Collapse the binary tree to 4-wide nodes in breadth-first order; returns the depth of the wide tree.
+static int collapse(const Builder &b, std::vector<pvb_bvh4_node> &wide) {
 
-extern "C" int pvb_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, int64_t n_faces,
-                             void *nodes_out, int64_t node_capacity, float *tris_out,
-                             int64_t *n_nodes_out, int32_t *max_depth_out) {
-    if (!verts || !faces || !nodes_out || !tris_out || n_faces < 1 || n_verts < 1) {
-        pvb_set_error("pvb_bvh_build: null argument or empty mesh (n_verts=%lld n_faces=%lld)",
-                      (long long)n_verts, (long long)n_faces);
-        return PVB_ERR_INVALID;
-    }
-    if (n_faces >= (1ll << 29)) {
-        pvb_set_error("pvb_bvh_build: too many faces (%lld)", (long long)n_faces);
-        return PVB_ERR_INVALID;
-    }
-    for (int64_t i = 0; i < 3 * n_faces; ++i)
-        if (faces[i] < 0 || faces[i] >= n_verts) {
-            pvb_set_error("pvb_bvh_build: face index %d out of range [0,%lld)", faces[i], (long long)n_verts);
-            return PVB_ERR_INVALID;
-        }
-
-    if (const char *e = getenv("PVB_BVH_LEAF")) {
-        const int v = atoi(e);
-        if (v >= 1 && v <= 4) kLeafMax = v;
-    }
-    Builder b;
-    b.verts = verts; b.faces = faces;
-    b.tbox.resize((size_t)n_faces);
-    b.cent.resize(3 * (size_t)n_faces);
-    b.order.resize((size_t)n_faces);
-    for (int64_t t = 0; t < n_faces; ++t) {
-        b.order[(size_t)t] = (int32_t)t;
-        Box bx; bx.reset();
-        for (int v = 0; v < 3; ++v) bx.grow(verts + 3 * (int64_t)faces[3 * t + v]);
-        b.tbox[(size_t)t] = bx;
-        for (int k = 0; k < 3; ++k) b.cent[3 * (size_t)t + k] = 0.5f * (bx.lo[k] + bx.hi[k]);
-    }
-    b.nodes.reserve(2 * (size_t)n_faces);
-    int bin_depth = 0;
-    b.build(0, (int)n_faces, 0, bin_depth);
-
-    // collapse to 4-wide nodes, breadth-first
-    std::vector<pvb_bvh4_node> wide;
     std::vector<int> wide_depth;
     struct Item { int bin; int wide; };
     std::queue<Item> q;
@@ -223,6 +182,68 @@ extern "C" int pvb_bvh_build(const float *verts, int64_t n_verts, const int32_t 
             n.hix[i] = c.box.hi[0]; n.hiy[i] = c.box.hi[1]; n.hiz[i] = c.box.hi[2];
             n.child[i] = link;
         }
+    }
+    return max_depth;
+}
+
+extern "C" int64_t pvb_bvh_max_nodes(int64_t n_faces) {
+    // every wide node has >= 2 children, leaves hold >= 1 triangle
+    return n_faces < 1 ? 1 : n_faces;
+}
+
+extern "C" int pvb_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, int64_t n_faces,
+                             void *nodes_out, int64_t node_capacity, float *tris_out,
+                             int64_t *n_nodes_out, int32_t *max_depth_out) {
+    if (!verts || !faces || !nodes_out || !tris_out || n_faces < 1 || n_verts < 1) {
+        pvb_set_error("pvb_bvh_build: null argument or empty mesh (n_verts=%lld n_faces=%lld)",
+                      (long long)n_verts, (long long)n_faces);
+        return PVB_ERR_INVALID;
+    }
+    if (n_faces >= (1ll << 29)) {
+        pvb_set_error("pvb_bvh_build: too many faces (%lld)", (long long)n_faces);
+        return PVB_ERR_INVALID;
+    }
+    for (int64_t i = 0; i < 3 * n_faces; ++i)
+        if (faces[i] < 0 || faces[i] >= n_verts) {
+            pvb_set_error("pvb_bvh_build: face index %d out of range [0,%lld)", faces[i], (long long)n_verts);
+            return PVB_ERR_INVALID;
+        }
+
+    if (const char *e = getenv("PVB_BVH_LEAF")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 4) kLeafMax = v;
+    }
+    Builder b;
+    b.verts = verts; b.faces = faces;
+    b.tbox.resize((size_t)n_faces);
+    b.cent.resize(3 * (size_t)n_faces);
+    b.order.resize((size_t)n_faces);
+    for (int64_t t = 0; t < n_faces; ++t) {
+        b.order[(size_t)t] = (int32_t)t;
+        Box bx; bx.reset();
+        for (int v = 0; v < 3; ++v) bx.grow(verts + 3 * (int64_t)faces[3 * t + v]);
+        b.tbox[(size_t)t] = bx;
+        for (int k = 0; k < 3; ++k) b.cent[3 * (size_t)t + k] = 0.5f * (bx.lo[k] + bx.hi[k]);
+    }
+    // The query kernels keep a fixed traversal stack: 3 * depth + 2 entries must fit (kMaxWideDepth).  SAH trees of
+    // ordinary meshes are far below that; a pathological one is rebuilt with balanced median splits.
+    constexpr int kMaxWideDepth = 20;
+    std::vector<pvb_bvh4_node> wide;
+    int max_depth = 1;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        b.force_median = attempt == 1;
+        b.nodes.clear();
+        b.nodes.reserve(2 * (size_t)n_faces);
+        for (int64_t t = 0; t < n_faces; ++t) b.order[(size_t)t] = (int32_t)t;
+        int bin_depth = 0;
+        b.build(0, (int)n_faces, 0, bin_depth);
+        wide.clear();
+        max_depth = collapse(b, wide);
+        if (max_depth <= kMaxWideDepth) break;
+    }
+    if (max_depth > kMaxWideDepth) {
+        pvb_set_error("pvb_bvh_build: tree depth %d exceeds the traversal stack even with balanced splits", max_depth);
+        return PVB_ERR_INVALID;
     }
     if ((int64_t)wide.size() > node_capacity) {
         pvb_set_error("pvb_bvh_build: node buffer too small (%lld > %lld)", (long long)wide.size(),

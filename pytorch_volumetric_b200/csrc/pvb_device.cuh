@@ -11,7 +11,7 @@
 
 namespace pvb {
 
-constexpr int kStack = 40;            // traversal stack entries per thread (builder bounds depth)
+constexpr int kStack = 64;            // traversal stack entries per thread; the builder bounds the depth at 20
 #define PVB_INF (__builtin_huge_valf())
 
 struct f3 { float x, y, z; };

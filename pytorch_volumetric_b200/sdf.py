@@ -175,7 +175,7 @@ class ObjectFactory(abc.ABC):
         st = self._dev.get(device)
         if st is None:
             nodes, tris, depth = self._bvh_host
-            if 3 * depth + 2 > 40:
+            if 3 * depth + 2 > 64:
                 raise nat.NativeLibraryError(f"BVH too deep for the traversal stack (depth {depth})")
             st = {
                 "nodes": torch.from_numpy(nodes).to(device),

@@ -73,7 +73,7 @@ def test_bvh_builder_invariants(name, built_lib):
     nodes = nodes_raw.view(np.float32).reshape(-1, 32)
     child = nodes_raw.view(np.int32).reshape(-1, 32)[:, 24:28]
     n_nodes = len(nodes)
-    assert 3 * depth + 2 <= 40
+    assert 3 * depth + 2 <= 64
     face_of = tris.view(np.int32)[:, 3]
     assert np.array_equal(np.sort(face_of), np.arange(len(f)))        # a permutation of the faces
     assert np.array_equal(tris[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]].reshape(-1, 3, 3), v32[f[face_of]])
