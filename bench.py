@@ -278,7 +278,7 @@ class C4(Workload):
     1.0), 200 joint configurations x 100 000 points; with N GPUs the configuration batch is sharded (strong
     scaling is reported by the driver from the per-N lines; per-GPU work = 200/N configurations)."""
     name = "c4"
-    kernel = "composed_query_kernel<false>"
+    kernel = "composed_cfgmajor_kernel | composed_query_kernel<false,2,16> (by configuration-tile fill)"
 
     def __init__(self, rank, world=1, n_cfg=200, n_pts=100_000, cache_dir=None, gather=False):
         import pytorch_volumetric_b200 as pv

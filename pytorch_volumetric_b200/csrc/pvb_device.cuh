@@ -469,13 +469,4 @@ __device__ __forceinline__ SdfOut sphere_eval(float radius, f3 p) {   // sdf.py:
     return o;
 }
 
-// Distance from p to the surface AABB of a sub-SDF: a lower bound of its value
-// whenever p lies outside the box.
-__device__ __forceinline__ float aabb_lower_bound(const pvb_sdf_desc &g, f3 p) {
-    const float dx = fmaxf(fmaxf(g.bb_min[0] - p.x, p.x - g.bb_max[0]), 0.f);
-    const float dy = fmaxf(fmaxf(g.bb_min[1] - p.y, p.y - g.bb_max[1]), 0.f);
-    const float dz = fmaxf(fmaxf(g.bb_min[2] - p.z, p.z - g.bb_max[2]), 0.f);
-    return sqrtf(dx * dx + dy * dy + dz * dz);
-}
-
 }  // namespace pvb
