@@ -84,6 +84,8 @@ __device__ __forceinline__ float box_d2(float lx, float ly, float lz, float hx, 
 // the better lane occupancy of the triangle code buys; runs of consecutive queries seeded with the previous closest
 // point, 11.4-15.9 ms.)
 #ifndef PVB_CLOSEST_WHILE_WHILE
+// 1: phase-aligned "while-while" walk.  Measured against the inline-leaf walk below (ms, mesh10k / C5 / C3):
+// 7.6 / 7.7 / 13.9 against 7.6 / 7.6 / 13.1 -- no gain: the cost is in the triangle tests themselves.
 #define PVB_CLOSEST_WHILE_WHILE 0
 #endif
 #if PVB_CLOSEST_WHILE_WHILE
