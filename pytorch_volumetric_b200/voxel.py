@@ -7,6 +7,10 @@ exact voxel lattice of the CachedSDF tables) and the third-party
 path and its callers use (`raw_data`, `shape`, `ensure_index_key`,
 `ravel_multi_index`, `get_valid_values`, `ensure_value_key`, `view[pts]`).
 """
+import abc
+import copy
+import math
+
 import numpy as np
 import torch
 
@@ -56,6 +60,8 @@ class GridView:
         return torch.round((key - self._min) / self._resolution).to(torch.long)
 
     def ensure_value_key(self, key, force=False):
+        if key.shape[-1] == 1 and self.dim > 1:      # flat (ravelled) indices, e.g. from raw_data.nonzero()
+            key = torch.stack(torch.unravel_index(key.reshape(-1), tuple(self.shape)), dim=-1)
         return key * self._resolution + self._min
 
     def get_valid_values(self, key):
@@ -93,7 +99,23 @@ class GridView:
         self._d[self.ravel_multi_index(idx[ok], self.shape)] = value
 
 
-class VoxelGrid:
+class Voxels(abc.ABC):
+    """Interface of the voxel containers (reference voxel.py:28-39)."""
+
+    @abc.abstractmethod
+    def get_known_pos_and_values(self):
+        """positions (N x d) and values (N) of the voxels that hold something"""
+
+    @abc.abstractmethod
+    def __getitem__(self, pts):
+        """values (N) at positions (N x d)"""
+
+    @abc.abstractmethod
+    def __setitem__(self, pts, value):
+        """store values (N) at positions (N x d)"""
+
+
+class VoxelGrid(Voxels):
     """Dense voxel container over a snapped range (reference voxel.py:42-91); used as the default
     lattice of ObjectFrameSDF.get_voxel_view."""
 
@@ -102,11 +124,26 @@ class VoxelGrid:
         self.invalid_val = 0
         self.dtype = dtype
         self.device = device
+        self._create_voxels(resolution, range_per_dim)
+
+    def _create_voxels(self, resolution, range_per_dim):
         self.range_per_dim = get_divisible_range_by_resolution(resolution, range_per_dim)
-        self.coords, self.pts = get_coordinates_and_points_in_grid(resolution, self.range_per_dim, device=device)
-        self._data = torch.zeros([len(c) for c in self.coords], dtype=dtype, device=device)
+        self.coords, self.pts = get_coordinates_and_points_in_grid(resolution, self.range_per_dim, device=self.device)
+        self._data = torch.zeros([len(c) for c in self.coords], dtype=self.dtype, device=self.device)
         self.voxels = GridView(self._data, self.range_per_dim, invalid_value=self.invalid_val)
         self.range_per_dim = np.array(self.range_per_dim)
+
+    def resize_to_fit(self):
+        """Shrink / move the grid so that it just contains the known voxels (one cell of slack per side)."""
+        pos, val = self.get_known_pos_and_values()
+        if pos.numel() == 0:
+            return
+        lo, hi = pos.min(dim=0).values, pos.max(dim=0).values
+        box = copy.deepcopy(self.range_per_dim)
+        for d in range(len(lo)):
+            box[d] = (lo[d].item() - self.resolution, hi[d].item() + self.resolution)
+        self._create_voxels(self.resolution, box)
+        self.__setitem__(pos, val)
 
     def get_voxel_center_points(self):
         return self.pts
@@ -125,3 +162,71 @@ class VoxelGrid:
 
     def __setitem__(self, pts, value):
         self.voxels[pts] = value
+
+
+class ExpandingVoxelGrid(VoxelGrid):
+    """VoxelGrid whose range grows, in whole cells, whenever a write falls outside it (reference voxel.py:94-117)."""
+
+    def __setitem__(self, pts, value):
+        if pts.numel() > 0:
+            lo, hi = pts.min(dim=0).values, pts.max(dim=0).values
+            box = copy.deepcopy(self.range_per_dim)
+            for d in range(len(lo)):
+                above = (hi[d] - self.range_per_dim[d][1]).item()
+                below = (self.range_per_dim[d][0] - lo[d]).item()
+                if above > 0:
+                    box[d][1] += math.ceil(above / self.resolution) * self.resolution
+                if below > 0:
+                    box[d][0] -= math.ceil(below / self.resolution) * self.resolution
+            if not np.allclose(box, self.range_per_dim):
+                pos, val = self.get_known_pos_and_values()      # carry the contents over to the larger grid
+                self._create_voxels(self.resolution, box)
+                super().__setitem__(pos, val)
+        return super().__setitem__(pts, value)
+
+
+class VoxelSet(Voxels):
+    """Explicit list of occupied positions and their values (reference voxel.py:120-134)."""
+
+    def __init__(self, positions, values):
+        self.positions = positions
+        self.values = values
+
+    def __getitem__(self, pts):
+        raise RuntimeError("Cannot get arbitrary points on a voxel set")
+
+    def __setitem__(self, pts, value):
+        self.positions = torch.cat((self.positions, pts.view(-1, self.positions.shape[-1])), dim=0)
+        self.values = torch.cat((self.values, value))
+
+    def get_known_pos_and_values(self):
+        return self.positions, self.values
+
+
+def bounds_contain_another_bounds(outer_bounds, inner_bounds):
+    outer_bounds, inner_bounds = np.asarray(outer_bounds), np.asarray(inner_bounds)
+    return bool(np.all(outer_bounds[:, 0] <= inner_bounds[:, 0]) and np.all(outer_bounds[:, 1] >= inner_bounds[:, 1]))
+
+
+def voxel_down_sample(points, resolution, range_per_dim=None, ignore_flat_dim=False):
+    """Down-sample an N x D cloud to the centres of the occupied cells of a grid of the given resolution
+    (reference voxel.py:141-171): all points are scattered into a boolean grid at once, the occupied cells are
+    read back.  Runs on the device the points live on."""
+    if points.shape[0] == 0:
+        return points
+    data_bounds = np.stack((points.min(dim=0)[0].cpu().numpy() - resolution * 2,
+                            points.max(dim=0)[0].cpu().numpy() + resolution * 2)).T
+    if range_per_dim is None or bounds_contain_another_bounds(range_per_dim, data_bounds):
+        range_per_dim = data_bounds
+    flat_z = ignore_flat_dim and range_per_dim[-1][0] == range_per_dim[-1][1]
+    flat_z_val = range_per_dim[-1][0]
+    if flat_z:
+        range_per_dim = range_per_dim[:-1]
+        points = points[..., :-1]
+    grid = VoxelGrid(resolution, range_per_dim, device=points.device, dtype=torch.bool)
+    grid[points] = 1
+    pts, _ = grid.get_known_pos_and_values()
+    pts = pts.to(points.dtype)
+    if flat_z:
+        pts = torch.cat((pts, torch.ones((pts.shape[0], 1), device=points.device, dtype=pts.dtype) * flat_z_val), dim=-1)
+    return pts
