@@ -1,8 +1,12 @@
 // pvb_kernels.cu -- sm_100a kernels and the C ABI of libpvb.so (see include/pvb.h).
 //
-// No tensor-core work anywhere on this path (there is no dense contraction);
-// the kernels are HBM-streaming (grid lookup, composed lookup) or
-// latency/L1-bound tree walks (mesh query, chamfer).
+// No tensor-core work anywhere on this path (there is no dense contraction).  The kernels are
+//   grid_lookup_tma / vec4 / scalar   HBM-streaming nearest-voxel lookup (CachedSDF)
+//   composed_query / composed_cfgmajor  transform + lookup / tree walk + min over sub-SDFs (ComposedSDF, RobotSDF)
+//   sort_hist / sort_scan / sort_scatter  Morton binning of large query batches
+//   mesh_query, chamfer_partial / finish  BVH4 tree walks (MeshSDF, chamfer)
+//   mesh_sample, sphere, transform_points  small helpers
+// Every tuning decision below carries its measurement in a comment; profiles/README.md has the full log.
 #include "pvb_device.cuh"
 
 #include <cstdarg>
