@@ -497,7 +497,7 @@ def main():
 
     rank, world, local = dist_setup(args.gpus)
     from pytorch_volumetric_b200 import _native
-    if _native.needs_build() and rank == 0:      # normally prebuilt by __graft_entry__.build(); the product never builds itself
+    if _native.lib_missing() and rank == 0:      # normally prebuilt by __graft_entry__.build(); the product never builds itself
         _native.build()
     barrier(world)
     sampler = ClockSampler(local)

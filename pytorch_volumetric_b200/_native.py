@@ -37,6 +37,10 @@ def needs_build():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+def lib_missing():
+    return not os.path.exists(LIB_PATH)
+
+
 def build(force=False, verbose=False):
     """nvcc-compile the sm_100a library in-tree (cross-compiles without a GPU)."""
     if not force and not needs_build():

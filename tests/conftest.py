@@ -14,7 +14,7 @@ def pytest_configure(config):
     # This is test scaffolding: the product itself never builds implicitly and raises when libpvb.so is missing.
     try:
         from pytorch_volumetric_b200 import _native
-        if _native.needs_build():
+        if _native.lib_missing():
             _native.build()
         from oracle import _geom
         _geom.build()
