@@ -48,6 +48,9 @@ enum {
                                       mesh query (mesh fields must be filled); default BOUNDING_BOX */
     PVB_GRID_PRUNE_OK   = 1u << 2, /* table verified to satisfy val >= dist(voxel centre, bb) - prune_margin:
                                       composed kernels may skip lookups that provably cannot win the min */
+    PVB_GRID_TRILINEAR  = 1u << 4, /* EXTENSION (not reference behaviour): value = trilinear interpolation of the
+                                      8 surrounding voxel values, gradient = analytic gradient of that interpolant
+                                      (cell-wise finite differences).  pvb_grid_lookup only. */
     PVB_MESH_CLOSED     = 1u << 3  /* every directed edge is matched by its reverse (closed, consistently oriented
                                       surface): crossing parity is direction independent, so the sign test may use
                                       the exact axis-aligned walk instead of the reference's diagonal ray */

@@ -393,3 +393,49 @@ def sample_mesh_points_port(mesh: MeshPort, num_points=100, seed=0, dtype=torch.
         pts = np.random.permutation(pts)[:num_points]                      # sdf.py:658
         normals = mesh.closest_point(pts, compute_normal=True)[3]          # sdf.py:660
     return torch.tensor(pts).to(dtype=dtype), normals.to(dtype=dtype)
+
+
+# ------------------------------------------------- extension: trilinear lookup
+def trilinear_lookup_port(table_val, ranges, bb, points):
+    """CPU restatement of the OPT-IN extension CachedSDF(interpolation="trilinear") of pytorch_volumetric_b200
+    (not reference behaviour; the reference only has the nearest-voxel rule above): value = trilinear
+    interpolation of the 8 surrounding voxel values, gradient = analytic gradient of the interpolant; points
+    failing all(min <= p <= max) take the AABB rule of sdf.py:555-571.  fp64 numpy."""
+    val = table_val.double().numpy()
+    n = np.array(val.shape)
+    lo = np.array([float(min(r)) for r in ranges]); hi = np.array([float(max(r)) for r in ranges])
+    res = (hi - lo) / np.maximum(n - 1, 1)
+    p = points.double().numpy().reshape(-1, 3)
+    inb = np.all((p >= lo) & (p <= hi), axis=1)
+    u = (p - lo) / res
+    c0 = np.clip(np.floor(u).astype(np.int64), 0, np.maximum(n - 2, 0))
+    f = np.clip(u - c0, 0.0, 1.0)
+    c1 = np.minimum(c0 + 1, n - 1)
+
+    def v(ix, iy, iz):
+        return val[ix, iy, iz]
+
+    x0, y0, z0 = c0[:, 0], c0[:, 1], c0[:, 2]
+    x1, y1, z1 = c1[:, 0], c1[:, 1], c1[:, 2]
+    fx, fy, fz = f[:, 0], f[:, 1], f[:, 2]
+    c00 = v(x0, y0, z0) * (1 - fz) + v(x0, y0, z1) * fz
+    c01 = v(x0, y1, z0) * (1 - fz) + v(x0, y1, z1) * fz
+    c10 = v(x1, y0, z0) * (1 - fz) + v(x1, y0, z1) * fz
+    c11 = v(x1, y1, z0) * (1 - fz) + v(x1, y1, z1) * fz
+    out_v = (c00 * (1 - fy) + c01 * fy) * (1 - fx) + (c10 * (1 - fy) + c11 * fy) * fx
+    gx = ((c10 * (1 - fy) + c11 * fy) - (c00 * (1 - fy) + c01 * fy)) / res[0]
+    gy = ((c01 - c00) * (1 - fx) + (c11 - c10) * fx) / res[1]
+    dz00 = v(x0, y0, z1) - v(x0, y0, z0); dz01 = v(x0, y1, z1) - v(x0, y1, z0)
+    dz10 = v(x1, y0, z1) - v(x1, y0, z0); dz11 = v(x1, y1, z1) - v(x1, y1, z0)
+    gz = ((dz00 * (1 - fy) + dz01 * fy) * (1 - fx) + (dz10 * (1 - fy) + dz11 * fy) * fx) / res[2]
+    out_g = np.stack([gx, gy, gz], axis=1)
+    # out of range: distance / direction to the surface AABB
+    bbn = np.asarray(bb, dtype=np.float64)
+    below = np.maximum(bbn[:, 0] - p, 0); above = np.maximum(p - bbn[:, 1], 0)
+    delta = np.where(bbn[:, 0] - p > 0, -(below + above), below + above)
+    dist = np.linalg.norm(delta, axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        gdir = delta / dist[:, None]
+    out_v = np.where(inb, out_v, dist)
+    out_g = np.where(inb[:, None], out_g, gdir)
+    return torch.from_numpy(out_v), torch.from_numpy(out_g), torch.from_numpy(inb)

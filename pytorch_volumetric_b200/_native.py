@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 PVB_KIND_GRID, PVB_KIND_MESH, PVB_KIND_SPHERE = 0, 1, 2
-PVB_GRID_INDEX_FP32, PVB_GRID_OOB_GT, PVB_GRID_PRUNE_OK, PVB_MESH_CLOSED = 1, 2, 4, 8
+PVB_GRID_INDEX_FP32, PVB_GRID_OOB_GT, PVB_GRID_PRUNE_OK, PVB_MESH_CLOSED, PVB_GRID_TRILINEAR = 1, 2, 4, 8, 16
 PVB_MESH_SIGNED, PVB_MESH_SURFACE_NORMAL, PVB_MESH_DEFAULT = 1, 2, 3
 
 

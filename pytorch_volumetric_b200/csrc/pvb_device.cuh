@@ -477,6 +477,21 @@ __device__ __noinline__ int grid_axis_index_exact(float pv, double min64, double
 //   * in-range gather is a predicated load; the point-to-AABB rule (sdf.py:555-571) is evaluated for every point
 //     with selects, its 1/dist by MUFU.RSQ + one Newton step (<= 1 ulp from the reference's sqrt + divide)
 // Returns the ravelled key through key_out (-1 when the point fails all(min <= p <= max)).
+// Point-to-AABB rule for out-of-range points (sdf.py:555-571), branch-free: delta = signed per-axis overshoot,
+// dist = |delta|, r = 1/dist by MUFU.RSQ + one Newton step (<= 1 ulp from the reference's sqrt + divide).
+__device__ __forceinline__ void aabb_rule(const pvb_sdf_desc &g, f3 p, float &dist, float &dx, float &dy, float &dz,
+                                          float &r) {
+    const float bx = g.bb_min[0] - p.x, by = g.bb_min[1] - p.y, bz = g.bb_min[2] - p.z;
+    const float ax = p.x - g.bb_max[0], ay = p.y - g.bb_max[1], az = p.z - g.bb_max[2];
+    const float tx = fmaxf(bx, 0.f) + fmaxf(ax, 0.f), ty = fmaxf(by, 0.f) + fmaxf(ay, 0.f),
+                tz = fmaxf(bz, 0.f) + fmaxf(az, 0.f);
+    dx = bx > 0.f ? -tx : tx; dy = by > 0.f ? -ty : ty; dz = bz > 0.f ? -tz : tz;
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    r = rsqrtf(d2);                                         // MUFU.RSQ; +inf at d2 == 0
+    r = r * fmaf(-0.5f * d2 * r, r, 1.5f);                  // one Newton step: 1/sqrt(d2) to ~1 ulp
+    dist = d2 > 0.f ? d2 * r : 0.f;                         // the reference yields 0 and NaN gradients here (0/0)
+}
+
 // kBranchOOB: skip the AABB rule with a branch when the point is in range (composed kernels, where out-of-range
 // points are rare and warps mostly agree) instead of evaluating it for every point with selects (streaming kernel,
 // 42 % out of range at C2: both sides would run anyway).
@@ -517,15 +532,8 @@ __device__ __forceinline__ SdfOut grid_eval(const pvb_sdf_desc &g, const NodeSta
         }
     }
     // point-to-AABB rule (sdf.py:555-571), branch-free
-    const float bx = g.bb_min[0] - p.x, by = g.bb_min[1] - p.y, bz = g.bb_min[2] - p.z;
-    const float ax = p.x - g.bb_max[0], ay = p.y - g.bb_max[1], az = p.z - g.bb_max[2];
-    const float tx = fmaxf(bx, 0.f) + fmaxf(ax, 0.f), ty = fmaxf(by, 0.f) + fmaxf(ay, 0.f),
-                tz = fmaxf(bz, 0.f) + fmaxf(az, 0.f);
-    const float dx = bx > 0.f ? -tx : tx, dy = by > 0.f ? -ty : ty, dz = bz > 0.f ? -tz : tz;
-    const float d2 = dx * dx + dy * dy + dz * dz;
-    float r = rsqrtf(d2);                                   // MUFU.RSQ; +inf at d2 == 0
-    r = r * fmaf(-0.5f * d2 * r, r, 1.5f);                  // one Newton step: 1/sqrt(d2) to ~1 ulp
-    const float dist = d2 > 0.f ? d2 * r : 0.f;             // the reference yields 0 and NaN gradients here (0/0)
+    float dist, dx, dy, dz, r;
+    aabb_rule(g, p, dist, dx, dy, dz, r);
     SdfOut o;
     o.val = inb ? e.x : dist;
     o.grad = mk3(inb ? e.y : dx * r, inb ? e.z : dy * r, inb ? e.w : dz * r);

@@ -428,6 +428,65 @@ grid_lookup_tma_kernel(const pvb_sdf_desc g, const float *__restrict__ pts, long
     if (tid == 0) bulk_wait_read<0>();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// EXTENSION, opt-in (CachedSDF(interpolation="trilinear")): the reference looks up the NEAREST voxel and a stored
+// gradient table (sdf.py:537-550), which is what every other kernel in this file reproduces.  This one
+// interpolates the value table trilinearly and returns the analytic gradient of the interpolant (per-cell finite
+// differences of the corner values) -- smoother for optimisation, not comparable to the reference within 1e-5
+// (the difference is O(resolution)); it is validated against its own CPU restatement (oracle/port.py).
+__global__ void __launch_bounds__(256)
+grid_trilinear_kernel(const pvb_sdf_desc g, const float *__restrict__ pts, long long n, float *__restrict__ out_val,
+                      float *__restrict__ out_grad) {
+    const float4 *tab = reinterpret_cast<const float4 *>(g.table);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int n0 = g.dims[0], n1 = g.dims[1], n2 = g.dims[2];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const f3 p = load_point(pts, i);
+        const bool inb = (p.x >= g.valid_lo[0]) & (p.x <= g.valid_hi[0]) & (p.y >= g.valid_lo[1]) &
+                         (p.y <= g.valid_hi[1]) & (p.z >= g.valid_lo[2]) & (p.z <= g.valid_hi[2]);
+        SdfOut o;
+        if (inb) {
+            const float u[3] = {(p.x - g.min32[0]) * g.inv_res32[0], (p.y - g.min32[1]) * g.inv_res32[1],
+                                (p.z - g.min32[2]) * g.inv_res32[2]};
+            const int nn[3] = {n0, n1, n2};
+            int c0[3];
+            float f[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                c0[a] = min(max((int)floorf(u[a]), 0), max(nn[a] - 2, 0));
+                f[a] = nn[a] > 1 ? fminf(fmaxf(u[a] - (float)c0[a], 0.f), 1.f) : 0.f;
+            }
+            const int s0 = n1 * n2, s1 = n2;
+            const int base = c0[0] * s0 + c0[1] * s1 + c0[2];
+            const int dx = n0 > 1 ? s0 : 0, dy = n1 > 1 ? s1 : 0, dz = n2 > 1 ? 1 : 0;
+            const float v000 = __ldg(tab + base).x, v001 = __ldg(tab + base + dz).x;
+            const float v010 = __ldg(tab + base + dy).x, v011 = __ldg(tab + base + dy + dz).x;
+            const float v100 = __ldg(tab + base + dx).x, v101 = __ldg(tab + base + dx + dz).x;
+            const float v110 = __ldg(tab + base + dx + dy).x, v111 = __ldg(tab + base + dx + dy + dz).x;
+            const float fx = f[0], fy = f[1], fz = f[2];
+            const float c00 = v000 + fz * (v001 - v000), c01 = v010 + fz * (v011 - v010);
+            const float c10 = v100 + fz * (v101 - v100), c11 = v110 + fz * (v111 - v110);
+            const float c0_ = c00 + fy * (c01 - c00), c1_ = c10 + fy * (c11 - c10);
+            o.val = c0_ + fx * (c1_ - c0_);
+            // d/dx: difference of the two y-z interpolated faces over the cell size, and likewise for y, z
+            const float gx = (c1_ - c0_) * g.inv_res32[0];
+            const float e0 = c01 - c00, e1 = c11 - c10;
+            const float gy = (e0 + fx * (e1 - e0)) * g.inv_res32[1];
+            const float z00 = v001 - v000, z01 = v011 - v010, z10 = v101 - v100, z11 = v111 - v110;
+            const float z0 = z00 + fy * (z01 - z00), z1 = z10 + fy * (z11 - z10);
+            const float gz = (z0 + fx * (z1 - z0)) * g.inv_res32[2];
+            o.grad = mk3(n0 > 1 ? gx : 0.f, n1 > 1 ? gy : 0.f, n2 > 1 ? gz : 0.f);
+        } else {
+            float dist, ex, ey, ez, r;        // out of range: the reference's AABB rule, unchanged
+            aabb_rule(g, p, dist, ex, ey, ez, r);
+            o.val = dist;
+            o.grad = mk3(ex * r, ey * r, ez * r);
+        }
+        out_val[i] = o.val;
+        out_grad[3 * i] = o.grad.x; out_grad[3 * i + 1] = o.grad.y; out_grad[3 * i + 2] = o.grad.z;
+    }
+}
+
 // scalar variant for the tail and for unaligned views
 template <bool kMesh>
 __global__ void __launch_bounds__(kGridThreads)
@@ -1125,6 +1184,15 @@ extern "C" int pvb_grid_lookup(const pvb_sdf_desc *grid, const float *pts, int64
     if (n == 0) return PVB_OK;
     const uint32_t mesh_mode = PVB_MESH_DEFAULT;
     const bool gt = (grid->flags & PVB_GRID_OOB_GT) != 0;
+    if (grid->flags & PVB_GRID_TRILINEAR) {
+        if (gt || out_outside || out_index || !out_val || !out_grad) {
+            pvb_set_error("pvb_grid_lookup: PVB_GRID_TRILINEAR supports value + gradient output with the AABB rule only");
+            return PVB_ERR_INVALID;
+        }
+        grid_trilinear_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(*grid, pts, n, out_val, out_grad);
+        PVB_CHECK_LAUNCH("pvb_grid_lookup(trilinear)");
+        return PVB_OK;
+    }
     auto aligned = [](const void *p, size_t a) { return p == nullptr || ((uintptr_t)p % a) == 0; };
     const bool vec_ok = aligned(pts, 16) && aligned(out_val, 16) && aligned(out_grad, 16) && aligned(out_outside, 4) &&
                         aligned(out_index, 16);

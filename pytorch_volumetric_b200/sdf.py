@@ -562,7 +562,7 @@ class CachedSDF(ObjectFrameSDF):
     def __init__(self, object_name, resolution, range_per_dim, gt_sdf: ObjectFrameSDF,
                  out_of_bounds_strategy=OutOfBoundsStrategy.BOUNDING_BOX,
                  device="cpu", clean_cache=False,
-                 debug_check_sdf=False, cache_path="sdf_cache.pkl"):
+                 debug_check_sdf=False, cache_path="sdf_cache.pkl", interpolation="nearest"):
         """
         :param object_name: readable name of the object; combined with the resolution and range for the cache key
         :param resolution: side length of each voxel cell
@@ -573,7 +573,13 @@ class CachedSDF(ObjectFrameSDF):
         :param clean_cache: ignore an existing cache entry and recompute
         :param debug_check_sdf: check the generated tables against the ground truth SDF
         :param cache_path: torch.save file holding {name: (val[nx,ny,nz], grad[Nvox,3])}, same format as the reference
+        :param interpolation: "nearest" (the reference's behaviour: nearest voxel value and stored gradient) or
+        "trilinear" -- an EXTENSION that interpolates the value table trilinearly and returns the gradient of the
+        interpolant (cell-wise finite differences); smoother, but O(resolution) away from the reference's output
         """
+        if interpolation not in ("nearest", "trilinear"):
+            raise ValueError(f"interpolation must be 'nearest' or 'trilinear', got {interpolation!r}")
+        self.interpolation = interpolation
         self.device = device
         self.voxels = None
         self.voxels_grad = None
@@ -694,13 +700,17 @@ class CachedSDF(ObjectFrameSDF):
             if math.isfinite(margin):
                 d.prune_margin = margin
                 flags |= nat.PVB_GRID_PRUNE_OK
+        if self.interpolation == "trilinear":
+            if self.out_of_bounds_strategy != OutOfBoundsStrategy.BOUNDING_BOX:
+                raise ValueError("interpolation='trilinear' supports OutOfBoundsStrategy.BOUNDING_BOX only")
+            flags = (flags | nat.PVB_GRID_TRILINEAR) & ~nat.PVB_GRID_PRUNE_OK
         d.flags = flags
         return d
 
     def native_desc(self, device):
         device = nat.compute_device(device)
-        if device != self._cdev:
-            return None
+        if device != self._cdev or self.interpolation != "nearest":
+            return None          # the fused composition kernels implement the reference's nearest-voxel rule only
         if self.out_of_bounds_strategy == OutOfBoundsStrategy.LOOKUP_GT_SDF and not self._gt_in_kernel:
             return None
         return self._desc
@@ -796,6 +806,7 @@ class CachedSDF(ObjectFrameSDF):
                              and not self._gt_in_kernel)
         if (torch.is_tensor(points_in_object_frame) and points_in_object_frame.device.type == "cpu"
                 and torch.device(self.device).type == "cpu" and not gt_outside_kernel and not self.debug_check_sdf
+                and self.interpolation == "nearest"
                 and points_in_object_frame.numel() // 3 >= self.host_pipeline_min_points):
             val, grad = self._host_pipeline(points_in_object_frame)
             dtype = points_in_object_frame.dtype

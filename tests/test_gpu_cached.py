@@ -167,3 +167,35 @@ def test_cached_c2_full_size_properties(tmp_path):
     # batch dims
     vb, gb = c(q[:6000].view(2, 30, 100, 3))
     assert vb.shape == (2, 30, 100) and gb.shape == (2, 30, 100, 3)
+
+
+def test_trilinear_extension_vs_its_cpu_restatement(tmp_path):
+    """Opt-in extension (not reference behaviour): trilinear value + gradient of the interpolant, checked against
+    oracle.port.trilinear_lookup_port (fp64) and through its defining properties."""
+    import pytorch_volumetric_b200 as pv
+    from oracle import port
+    z = golden("ref_cachedsdf_probe")
+    c = _cached_from_golden(z, "probe", tmp_path, interpolation="trilinear")
+    q = torch.from_numpy(z["q"]).cuda()
+    v, g = c(q)
+    shape = tuple(int(s) for s in z["table_shape"])
+    rv, rg, inb = port.trilinear_lookup_port(torch.from_numpy(z["table_val"]).reshape(shape), c.ranges,
+                                             z["bb"], q.cpu())
+    assert np.array_equal(inb.numpy(), z["inbound"])          # same in-range rule as the reference
+    assert (v.cpu().double() - rv).abs().max() < 2e-6
+    assert (g.cpu().double() - rg)[inb].abs().max() < 2e-3    # fp32 differences of ~1e-2 values over res = 2e-3
+    assert (g.cpu().double() - rg)[~inb].abs().max() < 1e-6
+    # exact at the voxel centres, continuous (Lipschitz) in between, within one cell of the nearest-voxel lookup
+    coords, centres = pv.get_coordinates_and_points_in_grid(float(z["resolution"]), c.ranges)
+    vc, _ = c(centres.cuda())
+    inside = c.voxel_keys(centres.cuda()) >= 0
+    assert (vc.cpu() - torch.from_numpy(z["table_val"]))[inside.cpu()].abs().max() < 1e-6
+    near = _cached_from_golden(z, "probe", tmp_path)
+    vn, _ = near(q)
+    assert (v - vn)[torch.from_numpy(z["inbound"]).cuda()].abs().max() < 2 * float(z["resolution"])
+    # the fused composition kernels keep the reference rule: a trilinear CachedSDF composes through the generic path
+    comp = pv.ComposedSDF([c], pv.Transform3d(matrix=torch.eye(4, device="cuda").unsqueeze(0)))
+    vcmp, _ = comp(q)
+    assert torch.equal(vcmp, v)
+    with pytest.raises(ValueError):
+        _cached_from_golden(z, "probe", tmp_path, interpolation="cubic")
