@@ -183,7 +183,13 @@ def test_trilinear_extension_vs_its_cpu_restatement(tmp_path):
                                              z["bb"], q.cpu())
     assert np.array_equal(inb.numpy(), z["inbound"])          # same in-range rule as the reference
     assert (v.cpu().double() - rv).abs().max() < 2e-6
-    assert (g.cpu().double() - rg)[inb].abs().max() < 1e-4    # fp32 differences of ~1e-2 values over res = 2e-3
+    # the gradient of a trilinear interpolant jumps across cell faces: compare away from the lattice planes (the
+    # query set deliberately contains exact voxel centres and cell-boundary points)
+    lo = np.array([float(min(r)) for r in c.ranges]); hi = np.array([float(max(r)) for r in c.ranges])
+    u = (q.cpu().double().numpy() - lo) / ((hi - lo) / (np.array(shape) - 1))
+    off_lattice = torch.from_numpy((np.abs(u - np.round(u)) > 1e-3).all(axis=1)) & inb
+    assert off_lattice.float().mean() > 0.4
+    assert (g.cpu().double() - rg)[off_lattice].abs().max() < 1e-4
     assert (g.cpu().double() - rg)[~inb].abs().max() < 1e-6
     # exact at the voxel centres, continuous (Lipschitz) in between, within one cell of the nearest-voxel lookup
     coords, centres = pv.get_coordinates_and_points_in_grid(float(z["resolution"]), c.ranges)
