@@ -731,9 +731,21 @@ class CachedSDF(ObjectFrameSDF):
             grad = torch.empty(n, 3, dtype=torch.float32, device=device) if want_val else None
             outside = torch.empty(n, dtype=torch.uint8, device=device) if want_outside else None
             index = torch.empty(n, dtype=torch.int64, device=device) if want_index else None
-            nat.check(nat.lib().pvb_grid_lookup(ctypes.byref(self._desc), nat.ptr(p), n, nat.ptr(val), nat.ptr(grad),
-                                                nat.ptr(outside), float(surface_level), nat.ptr(index),
-                                                nat.stream_ptr(device)), "pvb_grid_lookup")
+            L = nat.lib()
+            if self.interpolation == "trilinear" and (want_outside or want_index):
+                # keys / occupancy always follow the reference's nearest-voxel rule; values come from the interpolant
+                plain = self._desc.copy()
+                plain.flags &= ~nat.PVB_GRID_TRILINEAR
+                nat.check(L.pvb_grid_lookup(ctypes.byref(plain), nat.ptr(p), n, None, None, nat.ptr(outside),
+                                            float(surface_level), nat.ptr(index), nat.stream_ptr(device)),
+                          "pvb_grid_lookup")
+                if want_val:
+                    nat.check(L.pvb_grid_lookup(ctypes.byref(self._desc), nat.ptr(p), n, nat.ptr(val), nat.ptr(grad),
+                                                None, 0.0, None, nat.stream_ptr(device)), "pvb_grid_lookup")
+            else:
+                nat.check(L.pvb_grid_lookup(ctypes.byref(self._desc), nat.ptr(p), n, nat.ptr(val), nat.ptr(grad),
+                                            nat.ptr(outside), float(surface_level), nat.ptr(index),
+                                            nat.stream_ptr(device)), "pvb_grid_lookup")
         return p, val, grad, outside, index
 
     #: host batches at least this large are streamed through the GPU in chunks (copy-in / lookup / copy-out
