@@ -60,11 +60,15 @@ enum {
 enum {
     PVB_MESH_SIGNED         = 1u << 0, /* ray-parity inside test + sign (sdf.py:146-157) */
     PVB_MESH_SURFACE_NORMAL = 1u << 1, /* |d| < 1e-3 -> gradient = face normal (sdf.py:162-164) */
-    PVB_MESH_DEFAULT        = 3u
+    PVB_MESH_DEFAULT        = 3u,
+    PVB_MESH_WINDING        = 1u << 2  /* EXTENSION (not reference behaviour): with PVB_MESH_SIGNED, inside/outside from
+                                          the generalized winding number |w| > 1/2 (hierarchical first-order evaluation,
+                                          Barill et al. 2018) instead of crossing parity -- robust on open / self-
+                                          intersecting meshes; needs pvb_sdf_desc.wn_nodes */
 };
 
 /*
- * One queryable object.  232 bytes (pvb_sizeof_sdf_desc()), POD, host-resident (device pointers
+ * One queryable object.  240 bytes (pvb_sizeof_sdf_desc()), POD, host-resident (device pointers
  * inside); the composed kernels take a host array of these by value.
  *
  * GRID part  = CachedSDF state (sdf.py:521-525): interleaved table
@@ -107,6 +111,10 @@ typedef struct pvb_sdf_desc {
      * estimate provably rounds the same way as the exact formula); otherwise the exact formula above runs. */
     float inv_res32[3];
     float idx_certain[3];
+    /* ---- mesh: winding-number extension ----
+     * device float4[8 * n_nodes]: per node, for each of the 4 children {area-weighted centroid xyz, bounding
+     * radius} then {sum of area vectors xyz, 0}; NULL unless PVB_MESH_WINDING is used */
+    const void *wn_nodes;
 } pvb_sdf_desc;
 
 /* BVH4 node, 128 bytes: SoA child boxes + child links.

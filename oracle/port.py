@@ -439,3 +439,22 @@ def trilinear_lookup_port(table_val, ranges, bb, points):
     out_v = np.where(inb, out_v, dist)
     out_g = np.where(inb[:, None], out_g, gdir)
     return torch.from_numpy(out_v), torch.from_numpy(out_g), torch.from_numpy(inb)
+
+
+# ------------------------------------------- extension: winding-number sign
+def winding_number_port(vertices, faces, points, chunk=2000):
+    """Exact generalized winding number (sum of Van Oosterom-Strackee solid angles / 4 pi), fp64, brute force.
+    CPU restatement of the OPT-IN extension ObjectFactory.sign_mode = "winding" of pytorch_volumetric_b200 (not
+    reference behaviour: the reference uses crossing parity, sdf.py:146-157)."""
+    v = np.asarray(vertices, dtype=np.float32).astype(np.float64)      # the query structure holds fp32 vertices
+    tri = v[np.asarray(faces)]
+    q = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    out = np.empty(len(q))
+    for s0 in range(0, len(q), chunk):
+        d = tri[None] - q[s0:s0 + chunk, None, None, :]                 # (m, T, 3, 3)
+        A, B, C = d[:, :, 0], d[:, :, 1], d[:, :, 2]
+        la, lb, lc = (np.linalg.norm(x, axis=-1) for x in (A, B, C))
+        num = np.einsum("mti,mti->mt", A, np.cross(B, C))
+        den = la * lb * lc + (A * B).sum(-1) * lc + (B * C).sum(-1) * la + (C * A).sum(-1) * lb
+        out[s0:s0 + chunk] = (2.0 * np.arctan2(num, den)).sum(axis=1) / (4.0 * np.pi)
+    return out

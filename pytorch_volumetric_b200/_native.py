@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 PVB_KIND_GRID, PVB_KIND_MESH, PVB_KIND_SPHERE = 0, 1, 2
 PVB_GRID_INDEX_FP32, PVB_GRID_OOB_GT, PVB_GRID_PRUNE_OK, PVB_MESH_CLOSED, PVB_GRID_TRILINEAR = 1, 2, 4, 8, 16
-PVB_MESH_SIGNED, PVB_MESH_SURFACE_NORMAL, PVB_MESH_DEFAULT = 1, 2, 3
+PVB_MESH_SIGNED, PVB_MESH_SURFACE_NORMAL, PVB_MESH_DEFAULT, PVB_MESH_WINDING = 1, 2, 3, 4
 
 
 class NativeLibraryError(RuntimeError):
@@ -69,6 +69,7 @@ class SdfDesc(ctypes.Structure):
         ("nodes", ctypes.c_void_p), ("tris", ctypes.c_void_p), ("face_normals", ctypes.c_void_p),
         ("n_tris", ctypes.c_int32), ("ray_far", ctypes.c_float * 3), ("ray_seed", ctypes.c_uint32),
         ("radius", ctypes.c_float), ("inv_res32", ctypes.c_float * 3), ("idx_certain", ctypes.c_float * 3),
+        ("wn_nodes", ctypes.c_void_p),
     ]
 
     def copy(self):

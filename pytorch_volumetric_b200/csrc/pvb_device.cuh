@@ -395,6 +395,58 @@ __device__ __forceinline__ int bvh_parity_x(const float4 *__restrict__ gnodes, c
 }
 
 // ----------------------------------------------------------------------------
+// EXTENSION, opt-in (ObjectFactory.sign_mode = "winding"): generalized winding number of the triangle soup at q,
+// w(q) = (1 / 4 pi) * sum of signed solid angles.  The reference decides inside/outside by crossing parity
+// (sdf.py:146-157), which is what the default path reproduces; parity is meaningless on open or self-intersecting
+// surfaces, the winding number degrades gracefully there.  Hierarchical evaluation (Barill, Dickson, Schmidt, Levin,
+// Jacobson 2018, first-order term): a subtree whose bounding sphere (centre = area-weighted centroid p~, radius r)
+// is farther than beta * r is replaced by the dipole (p~ - q) . N / |p~ - q|^3 with N the sum of its area vectors;
+// near subtrees are opened, leaves use the exact Van Oosterom-Strackee solid angle.
+__device__ __forceinline__ float bvh_winding(const float4 *__restrict__ gnodes, const float4 *__restrict__ wn,
+                                             const NodeStage &st, const float4 *__restrict__ tris, f3 q) {
+    constexpr float kBeta2 = 4.f;          // beta = 2
+    float w = 0.f;
+    int stack_n[kStack];
+    int sp = 0;
+    stack_n[sp++] = 0;
+    while (sp > 0) {
+        const int ni = stack_n[--sp];
+        const int4 ch = *reinterpret_cast<const int4 *>(node_ptr(gnodes, st, ni) + 6);
+        const int c[4] = {ch.x, ch.y, ch.z, ch.w};
+        const float4 *wv = wn + 8 * (size_t)ni;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c[k] == INT32_MIN) continue;
+            const float4 pr = __ldg(wv + k), nn = __ldg(wv + 4 + k);
+            const f3 dlt = mk3(pr.x - q.x, pr.y - q.y, pr.z - q.z);
+            const float d2 = dot(dlt, dlt);
+            if (d2 > kBeta2 * pr.w * pr.w) {                 // far: dipole
+                w += dot(dlt, mk3(nn.x, nn.y, nn.z)) * rsqrtf(d2) / d2;
+                continue;
+            }
+            if (c[k] >= 0) {
+                if (sp < kStack) stack_n[sp++] = c[k];
+                continue;
+            }
+            const unsigned code = (unsigned)~c[k];
+            const int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
+            for (int t = first; t < first + cnt; ++t) {
+                const float4 v0 = __ldg(tris + 3 * (size_t)t), v1 = __ldg(tris + 3 * (size_t)t + 1),
+                             v2 = __ldg(tris + 3 * (size_t)t + 2);
+                const f3 A = mk3(v0.x - q.x, v0.y - q.y, v0.z - q.z), B = mk3(v1.x - q.x, v1.y - q.y, v1.z - q.z),
+                         C = mk3(v2.x - q.x, v2.y - q.y, v2.z - q.z);
+                const float la = sqrtf(dot(A, A)), lb = sqrtf(dot(B, B)), lc = sqrtf(dot(C, C));
+                const float num = A.x * (B.y * C.z - B.z * C.y) - A.y * (B.x * C.z - B.z * C.x) +
+                                  A.z * (B.x * C.y - B.y * C.x);
+                const float den = la * lb * lc + dot(A, B) * lc + dot(B, C) * la + dot(C, A) * lb;
+                w += 2.f * atan2f(num, den);                 // solid angle of the triangle seen from q
+            }
+        }
+    }
+    return w * 0.07957747154594767f;                          // 1 / (4 pi)
+}
+
+// ----------------------------------------------------------------------------
 // Deterministic stand-in for the reference's unseeded ray jitter (sdf.py:149):
 // three ~N(0,1) numbers per point from an integer hash (sum of four 16-bit
 // uniforms), every step exact in fp32 so that a host mirror reproduces it.

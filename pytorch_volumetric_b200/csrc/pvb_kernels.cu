@@ -272,6 +272,36 @@ mesh_query_kernel(const pvb_sdf_desc m, const float *__restrict__ pts, long long
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// EXTENSION (sign_mode="winding"): second pass over the result of an UNSIGNED mesh_query_kernel launch.  Keeps the
+// hot kernel free of the third tree walk: inside/outside from the generalized winding number, then the reference's
+// epilogue (sign of the distance, direction of the gradient, face normal inside the 1e-3 shell; sdf.py:154-164).
+__global__ void __launch_bounds__(256)
+mesh_winding_kernel(const pvb_sdf_desc m, const float *__restrict__ pts, long long n,
+                    const uint32_t *__restrict__ perm, uint32_t mode, float *__restrict__ dist,
+                    float *__restrict__ grad, const int *__restrict__ face) {
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    const float4 *nodes = reinterpret_cast<const float4 *>(m.nodes);
+    const float4 *tris = reinterpret_cast<const float4 *>(m.tris);
+    const float4 *wn = reinterpret_cast<const float4 *>(m.wn_nodes);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const long long i = perm ? (long long)perm[j] : j;
+        const f3 p = load_point(pts, i);
+        // consistently oriented surface: w = +1 inside for outward normals, -1 for inward ones
+        const bool inside = fabsf(bvh_winding(nodes, wn, st, tris, p)) > 0.5f;
+        float d = dist[i];                               // unsigned pass: d >= 0, gradient points away from the surface
+        f3 g = mk3(grad[3 * i], grad[3 * i + 1], grad[3 * i + 2]);
+        if (inside) { d = -d; g = mk3(-g.x, -g.y, -g.z); }
+        if ((mode & PVB_MESH_SURFACE_NORMAL) && fabsf(d) < 1e-3f && face[i] >= 0) {
+            const float *fn = m.face_normals + 3 * (size_t)face[i];
+            g = mk3(__ldg(fn), __ldg(fn + 1), __ldg(fn + 2));
+        }
+        dist[i] = d;
+        grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z;
+    }
+}
+
 // =============================================================== grid lookup
 // Streaming kernel: 28 B of compulsory HBM traffic per point (12 in, 16 out);
 // the table (16 B/voxel, interleaved {val,gx,gy,gz}) stays L2 resident.
@@ -1158,10 +1188,22 @@ extern "C" int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_
     long long run = n / ((long long)sm_count() * 2048);
     run = run < 1 ? 1 : (run > run_max ? run_max : run);
     const int blocks = grid_for((n + run - 1) / run, kMeshThreads, 8);
-    mesh_query_kernel<<<blocks, kMeshThreads, smem, (cudaStream_t)stream>>>(*mesh, pts, n, perm, (int)run, mode, n_stage,
-                                                                            out_dist, out_grad, out_closest, out_face,
-                                                                            out_normal);
+    const bool winding = (mode & PVB_MESH_WINDING) && (mode & PVB_MESH_SIGNED);
+    if (winding && (!mesh->wn_nodes || !out_face)) {
+        pvb_set_error("pvb_mesh_query: PVB_MESH_WINDING needs pvb_sdf_desc.wn_nodes and an out_face buffer");
+        return PVB_ERR_INVALID;
+    }
+    // winding mode: unsigned first pass (distance >= 0, gradient away from the surface), sign in a second pass
+    const uint32_t walk_mode = winding ? 0u : (mode & ~(uint32_t)PVB_MESH_WINDING);
+    mesh_query_kernel<<<blocks, kMeshThreads, smem, (cudaStream_t)stream>>>(*mesh, pts, n, perm, (int)run, walk_mode,
+                                                                            n_stage, out_dist, out_grad, out_closest,
+                                                                            out_face, out_normal);
     PVB_CHECK_LAUNCH("pvb_mesh_query");
+    if (winding) {
+        mesh_winding_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(*mesh, pts, n, perm, mode, out_dist,
+                                                                                  out_grad, out_face);
+        PVB_CHECK_LAUNCH("pvb_mesh_query(winding)");
+    }
     return PVB_OK;
 }
 

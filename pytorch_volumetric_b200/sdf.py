@@ -80,6 +80,61 @@ def _as_trimesh(mesh):
     raise TypeError("mesh= expects (vertices, faces) or an object with .vertices and .triangles")
 
 
+def _winding_moments(nodes_u8, tris):
+    """Per BVH4 node and child: area-weighted centroid + bounding radius and the sum of area vectors -- the
+    first-order data of the hierarchical winding-number evaluation (EXTENSION, see pvb.h PVB_MESH_WINDING).
+    nodes_u8 (n,128) uint8 and tris (F,12) float32 are the arrays pvb_bvh_build returned.  -> float32 (n, 8, 4)."""
+    n = nodes_u8.shape[0]
+    nf = nodes_u8.view(np.float32).reshape(n, 32).astype(np.float64)
+    child = nodes_u8.view(np.int32).reshape(n, 32)[:, 24:28].astype(np.int64)
+    lo = np.stack([nf[:, 0:4], nf[:, 4:8], nf[:, 8:12]], axis=-1)          # (n, 4, 3)
+    hi = np.stack([nf[:, 12:16], nf[:, 16:20], nf[:, 20:24]], axis=-1)
+    t = tris.astype(np.float64)
+    v0, v1, v2 = t[:, 0:3], t[:, 4:7], t[:, 8:11]
+    avec = 0.5 * np.cross(v1 - v0, v2 - v0)                                # area vectors
+    area = np.linalg.norm(avec, axis=1)
+    acen = area[:, None] * (v0 + v1 + v2) / 3.0
+    cs = lambda a: np.concatenate([np.zeros((1,) + a.shape[1:]), np.cumsum(a, axis=0)])   # prefix sums, leaf order
+    cs_vec, cs_area, cs_cen = cs(avec), cs(area), cs(acen)
+    empty = child == -2 ** 31
+    leaf = (child < 0) & ~empty
+    inner = child >= 0
+    code = np.where(leaf, ~child, 0)
+    first, cnt = code >> 2, (code & 3) + 1
+    N = np.zeros((n, 4, 3)); A = np.zeros((n, 4)); C = np.zeros((n, 4, 3))
+    N[leaf] = (cs_vec[(first + cnt)[leaf]] - cs_vec[first[leaf]])
+    A[leaf] = (cs_area[(first + cnt)[leaf]] - cs_area[first[leaf]])
+    C[leaf] = (cs_cen[(first + cnt)[leaf]] - cs_cen[first[leaf]])
+    # inner children: totals of the child node; children have larger indices (BFS layout), so sweep by depth
+    depth = np.zeros(n, dtype=np.int64)
+    for i in range(n):                       # parents precede children
+        ch = child[i][inner[i]]
+        depth[ch] = depth[i] + 1
+    for dlev in range(int(depth.max()), -1, -1):
+        idx = np.nonzero(depth == dlev)[0]
+        if dlev < depth.max():
+            sel = inner[idx]
+            ii, kk = np.nonzero(sel)
+            cidx = child[idx[ii], kk]
+            N[idx[ii], kk] = N[cidx].sum(axis=1)
+            A[idx[ii], kk] = A[cidx].sum(axis=1)
+            C[idx[ii], kk] = C[cidx].sum(axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        cen = C / A[..., None]
+    with np.errstate(invalid="ignore"):
+        box_c = 0.5 * (lo + hi)
+    bad = ~np.isfinite(cen).all(axis=-1) | (A <= 0)
+    cen[bad] = np.where(np.isfinite(box_c[bad]), box_c[bad], 0.0)
+    with np.errstate(invalid="ignore"):
+        rad = np.linalg.norm(np.maximum(np.abs(cen - lo), np.abs(hi - cen)), axis=-1)
+    rad[empty] = 0.0
+    out = np.zeros((n, 8, 4), dtype=np.float32)
+    out[:, 0:4, 0:3] = np.where(empty[..., None], 0.0, cen)
+    out[:, 0:4, 3] = np.where(np.isfinite(rad), rad, 0.0)
+    out[:, 4:8, 0:3] = np.where(empty[..., None], 0.0, N)
+    return out
+
+
 class ObjectFactory(abc.ABC):
     def __init__(self, name='', scale=1.0, vis_frame_pos=(0, 0, 0), vis_frame_rot=(0, 0, 0, 1),
                  plausible_suboptimality=0.001, mesh=None, ray_seed=0, **kwargs):
@@ -196,8 +251,18 @@ class ObjectFactory(abc.ABC):
         self._fill_mesh_part(d, st)
         return d
 
+    def _winding_state(self, device):
+        st = self._device_state(device)
+        if "wn" not in st:
+            nodes, tris, _ = self._bvh_host
+            st["wn"] = torch.from_numpy(_winding_moments(nodes, tris)).to(st["nodes"].device)
+        return st["wn"]
+
     #: set False to force the reference's diagonal ray (sdf.py:147-153) even on closed meshes
     axis_ray_when_closed = True
+    #: "parity" (the reference's rule: odd number of ray crossings => inside) or "winding" -- an EXTENSION that
+    #: classifies by the generalized winding number |w| > 1/2, robust on open / self-intersecting meshes
+    sign_mode = "parity"
 
     def _fill_mesh_part(self, d, st):
         d.nodes = st["nodes"].data_ptr()
@@ -239,9 +304,16 @@ class ObjectFactory(abc.ABC):
             closest = torch.empty(n, 3, dtype=torch.float32, device=device)
             normal = torch.empty(n, 3, dtype=torch.float32, device=device) if compute_normal else None
             desc = self.native_desc(device)
+            face = None
+            if self.sign_mode == "winding" and (mode & nat.PVB_MESH_SIGNED):
+                mode |= nat.PVB_MESH_WINDING
+                desc.wn_nodes = self._winding_state(device).data_ptr()
+                face = torch.empty(n, dtype=torch.int32, device=device)
+            elif self.sign_mode != "parity":
+                raise ValueError(f"sign_mode must be 'parity' or 'winding', got {self.sign_mode!r}")
             ws = nat.query_workspace(n, device)
             nat.check(nat.lib().pvb_mesh_query(ctypes.byref(desc), nat.ptr(p), n, mode, nat.ptr(dist), nat.ptr(grad),
-                                               nat.ptr(closest), None, nat.ptr(normal), nat.ptr(ws),
+                                               nat.ptr(closest), nat.ptr(face), nat.ptr(normal), nat.ptr(ws),
                                                ws.numel() if ws is not None else 0, nat.stream_ptr(device)),
                       "pvb_mesh_query")
 
@@ -376,6 +448,8 @@ class MeshSDF(ObjectFrameSDF):
         return res.distance, res.gradient
 
     def native_desc(self, device):
+        if self.obj_factory.sign_mode != "parity":
+            return None      # the fused composition kernels implement the reference's parity rule only
         return self.obj_factory.native_desc(device)
 
 

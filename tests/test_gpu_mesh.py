@@ -123,3 +123,39 @@ def test_mesh_query_large_properties():
     rs = 0.1 * (1 + 0.25 * torch.sin(5 * th) * torch.sin(4 * phi))
     clear = (r - rs).abs() > 0.004          # away from the faceting error of the triangulation
     assert torch.equal((res.distance < 0)[clear], (r < rs)[clear])
+
+
+@pytest.mark.parametrize("name", ["probe", "wrench", "scene_overlap"])
+def test_winding_sign_extension(name):
+    """Opt-in extension (not reference behaviour): inside/outside from the generalized winding number, checked
+    against the exact fp64 brute-force sum (oracle.port.winding_number_port)."""
+    from oracle import port
+    v, f = workloads.fixture_mesh(name)
+    n = 6000
+    pts = _query_points(name, n, seed=33)
+    par = pv_factory(name)
+    win = pv_factory(name)
+    win.sign_mode = "winding"
+    rp = par.object_frame_closest_point(pts.cuda())
+    rw = win.object_frame_closest_point(pts.cuda())
+    # same unsigned distance, closest point and (away from the 1e-3 shell) the same gradient up to sign
+    assert torch.equal(rp.distance.abs(), rw.distance.abs()) and torch.equal(rp.closest, rw.closest)
+    w_exact = port.winding_number_port(v, f, pts.numpy())
+    clear = np.abs(np.abs(w_exact) - 0.5) > 0.05           # the first-order far field is good to ~1e-2
+    inside_gpu = (rw.distance < 0).cpu().numpy()
+    assert np.array_equal(inside_gpu[clear], (np.abs(w_exact) > 0.5)[clear])
+    assert clear.mean() > 0.97
+    flipped = (rp.distance < 0) != (rw.distance < 0)
+    if par.is_closed and name != "scene_overlap":
+        assert int(flipped.sum()) == 0                      # closed single surface: parity == winding
+    if name == "scene_overlap":
+        # inside both boxes: two crossings (parity says outside), winding number 2 (inside)
+        assert int(flipped.sum()) > 0 and np.all(np.round(w_exact[flipped.cpu().numpy()]) == 2)
+    g_flip = rw.gradient[flipped] + rp.gradient[flipped]
+    far = (rw.distance[flipped].abs() > 1e-3)
+    assert g_flip[far].abs().max() < 1e-6 if far.any() else True
+    # a winding-mode MeshSDF composes through the generic path
+    import pytorch_volumetric_b200 as pv
+    comp = pv.ComposedSDF([pv.MeshSDF(win)], pv.Transform3d(matrix=torch.eye(4, device="cuda").unsqueeze(0)))
+    vc, _ = comp(pts.cuda())
+    assert torch.equal(vc, rw.distance)
