@@ -106,6 +106,11 @@ def test_composed_fused_equals_generic_path(tmp_path):
     twin = pv.ComposedSDF([sdfs[0], sdfs[0]], pv.Transform3d(matrix=tmat[:1].repeat(2, 1, 1)))
     _, _, w = twin.query(q, return_which=True)
     assert int(w.max()) == 0
+    # ... also when the kernel visits the sub-SDFs out of index order (bit-reversed: 0, 2, 1, 3, and 0, 4, 2, 6, ...)
+    for n_same in (3, 4, 7):
+        same = pv.ComposedSDF([sdfs[0]] * n_same, pv.Transform3d(matrix=tmat[:1].repeat(n_same, 1, 1)))
+        _, _, w = same.query(q, return_which=True)
+        assert int(w.max()) == 0
 
 
 def test_composed_of_meshes_vs_oracle():
