@@ -283,8 +283,9 @@ class C4(Workload):
     def __init__(self, rank, world=1, n_cfg=200, n_pts=100_000, cache_dir=None, gather=False):
         import pytorch_volumetric_b200 as pv
         from pytorch_volumetric_b200 import distributed as pd
-        self.gather = gather and world > 1
+        self.gather = gather if world > 1 else False
         self.pd = pd
+        self.peer = pd.PeerResult(n_cfg, n_pts) if self.gather == "peer" else None
         d = os.path.join(cache_dir or tempfile.gettempdir(), f"pvb_bench_arm_{rank}")
         urdf, end = workloads.write_arm(d)
         chain = pv.build_serial_chain_from_urdf(open(urdf).read(), end).to(device="cuda")
@@ -309,10 +310,14 @@ class C4(Workload):
                                  f"{n_vox} voxels = {16 * n_vox / 1e6:.0f} MB tables) x {n_cfg} configurations x "
                                  f"{n_pts} points, configurations sharded over ranks",
                      "configs_this_rank": self.end - self.begin, "l2_policy": "output 320 MB/step > L2",
-                     "result_reassembly": "all-gather of the per-rank slabs (NCCL)" if self.gather else
-                     "none: every rank keeps its configuration slab"}
+                     "result_reassembly": {True: "all-gather of the per-rank slabs (NCCL)",
+                                           "peer": "kernel epilogue stores every slab into all ranks' buffers over "
+                                                   "NVLink (peer-mapped, CUDA IPC) + one 4-byte all-reduce as barrier",
+                                           False: "none: every rank keeps its configuration slab"}[self.gather]}
 
     def step(self, i):
+        if self.gather == "peer":   # full result on every rank, written by the kernels themselves
+            return self.pd.sharded_robot_query(self.robot, self.dev[i % 3], gather="peer", result=self.peer)
         if self.gather:      # every rank ends up with the full (200, M) result: one NCCL all-gather per tensor
             return self.pd.sharded_robot_query(self.robot, self.dev[i % 3], gather=True)
         return self.robot.sdf.query(self.dev[i % 3], cfg_begin=self.begin, cfg_count=self.end - self.begin)
@@ -416,6 +421,8 @@ def make_workload(name, rank, world):
         return C4(rank, world)
     if name == "c4gather":
         return C4(rank, world, gather=True)
+    if name == "c4peer":
+        return C4(rank, world, gather="peer")
     if name == "c4readme":
         return C4(rank, world, n_cfg=200, n_pts=15251)
     if name == "c5":

@@ -177,6 +177,36 @@ int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_m
                        const float *pts, int64_t n_pts, uint32_t mesh_mode,
                        float *out_val, float *out_grad, int32_t *out_which, void *stream);
 
+/* ---- the same query with the result slab stored to several destinations from the kernel epilogue ----
+ * Multi-GPU re-assembly of a configuration-sharded RobotSDF result (model_to_sdf.py:117-125 returns the full
+ * (|A|, N) tensors): every rank evaluates its slab [cfg_begin, cfg_begin + cfg_count) and writes it straight into
+ * the full-size result buffer of every rank -- its own and the peer-mapped ones (pvb_ipc_open) -- so the NVLink
+ * traffic overlaps the lookups instead of following them as a separate all-gather.
+ * targets: HOST array of n_targets (1..PVB_MAX_TARGETS) DEVICE pointer pairs, each already advanced to the slab
+ * (element cfg_begin * n_pts of that rank's full buffer); target 0 conventionally is the local buffer.  The caller
+ * orders the launch after the peers' previous readers and publishes completion (stream-ordered collective or
+ * event) before anyone reads. */
+#define PVB_MAX_TARGETS 8
+typedef struct pvb_out_target {
+    float *val;  /* [cfg_count * n_pts]     */
+    float *grad; /* [cfg_count * n_pts * 3] */
+} pvb_out_target;
+int pvb_composed_query_multi(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
+                             int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count,
+                             const float *pts, int64_t n_pts, uint32_t mesh_mode,
+                             const pvb_out_target *targets, int32_t n_targets, int32_t *out_which, void *stream);
+
+/* ---- peer-visible device buffers (one process per GPU, same node) ----
+ * pvb_ipc_alloc: cudaMalloc on the current device (IPC handles need a whole allocation, not a slice of a caching
+ * allocator's segment); pvb_ipc_export fills a 64-byte handle another PROCESS passes to pvb_ipc_open to map the
+ * buffer (peer access is enabled on first use).  pvb_ipc_close unmaps, pvb_ipc_free releases the allocation. */
+#define PVB_IPC_HANDLE_BYTES 64
+int pvb_ipc_alloc(int64_t bytes, void **out_ptr);
+int pvb_ipc_free(void *ptr);
+int pvb_ipc_export(void *ptr, unsigned char *handle /* [PVB_IPC_HANDLE_BYTES] */);
+int pvb_ipc_open(const unsigned char *handle, void **out_ptr);
+int pvb_ipc_close(void *ptr);
+
 /* ---- batch_chamfer_dist, chamfer.py:79-94 ----
  * world_to_object DEVICE float[n_tf][16]; pts DEVICE [n_pts,3] world frame;
  * workspace DEVICE float[n_tf * pvb_chamfer_workspace(n_pts)]; out DEVICE float[n_tf]

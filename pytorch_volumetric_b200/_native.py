@@ -78,6 +78,14 @@ class SdfDesc(ctypes.Structure):
         return other
 
 
+class OutTarget(ctypes.Structure):
+    """Mirror of pvb_out_target (include/pvb.h)."""
+    _fields_ = [("val", ctypes.c_void_p), ("grad", ctypes.c_void_p)]
+
+
+MAX_TARGETS = 8
+IPC_HANDLE_BYTES = 64
+
 _lib = None
 
 _SIGNATURES = {
@@ -103,6 +111,15 @@ _SIGNATURES = {
                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pvb_composed_query_multi": (ctypes.c_int, [ctypes.POINTER(SdfDesc), ctypes.c_int32, ctypes.c_int32,
+                                                ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p,
+                                                ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    "pvb_ipc_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]),
+    "pvb_ipc_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "pvb_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    "pvb_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "pvb_ipc_close": (ctypes.c_int, [ctypes.c_void_p]),
     "pvb_chamfer_workspace": (ctypes.c_int64, [ctypes.c_int64]),
     "pvb_chamfer": (ctypes.c_int, [ctypes.POINTER(SdfDesc), ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
                                    ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,

@@ -603,12 +603,22 @@ static void fill_order(DescPack<MAXS> &pack, int n) {
     if (plain) for (int i = 0; i < n; ++i) pack.order[i] = (unsigned char)i;
 }
 
-template <bool kMesh, int PTS, int MAXS>
+// Destinations of the multi-target variants (kMulti): the local result buffer and the peer-mapped buffers of the
+// other ranks, each already advanced to this rank's configuration slab.  Stores to peer memory travel over NVLink
+// while the kernel keeps evaluating, so a configuration-sharded RobotSDF result is re-assembled on every rank
+// without a trailing all-gather.
+struct OutTargets {
+    float *val[PVB_MAX_TARGETS];
+    float *grad[PVB_MAX_TARGETS];
+    int n;
+};
+
+template <bool kMesh, int PTS, int MAXS, bool kMulti>
 __global__ void __launch_bounds__(kCompThreads, (kMesh ? PVB_COMPMESH_MINB : (PTS > 1 ? PVB_COMP_MINB : 1)))
 composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, const float *__restrict__ xforms,
                       int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, long long first_pt,
                       long long n_pts, uint32_t mesh_mode, float *__restrict__ out_val, float *__restrict__ out_grad,
-                      int *__restrict__ out_which) {
+                      int *__restrict__ out_which, const __grid_constant__ OutTargets tg) {
     __shared__ __align__(16) float s_xf[kCompSmemXf][12];
     const bool use_smem = n_sdf <= kCompSmemXf;
     NodeStage st; st.smem = nullptr; st.n = 0;
@@ -760,24 +770,33 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
                             fmaf(bg[k].x, r0.z, fmaf(bg[k].y, r1.z, bg[k].z * r2.z)));
             }
             const long long o_i = (long long)c * n_pts + i0;
-            if constexpr (PTS == 4) {
-                __stcs(reinterpret_cast<float4 *>(out_val + o_i), make_float4(best[0], best[1], best[2], best[3]));
-                float4 *dg = reinterpret_cast<float4 *>(out_grad + 3 * o_i);
-                __stcs(dg, make_float4(go[0].x, go[0].y, go[0].z, go[1].x));
-                __stcs(dg + 1, make_float4(go[1].y, go[1].z, go[2].x, go[2].y));
-                __stcs(dg + 2, make_float4(go[2].z, go[3].x, go[3].y, go[3].z));
-                if (out_which) *reinterpret_cast<int4 *>(out_which + o_i) = make_int4(bs[0], bs[1], bs[2], bs[3]);
-            } else if constexpr (PTS == 2) {
-                __stcs(reinterpret_cast<float2 *>(out_val + o_i), make_float2(best[0], best[1]));
-                float2 *dg = reinterpret_cast<float2 *>(out_grad + 3 * o_i);
-                __stcs(dg, make_float2(go[0].x, go[0].y));
-                __stcs(dg + 1, make_float2(go[0].z, go[1].x));
-                __stcs(dg + 2, make_float2(go[1].y, go[1].z));
-                if (out_which) *reinterpret_cast<int2 *>(out_which + o_i) = make_int2(bs[0], bs[1]);
+            auto emit = [&](float *ov, float *og) {
+                if constexpr (PTS == 4) {
+                    __stcs(reinterpret_cast<float4 *>(ov + o_i), make_float4(best[0], best[1], best[2], best[3]));
+                    float4 *dg = reinterpret_cast<float4 *>(og + 3 * o_i);
+                    __stcs(dg, make_float4(go[0].x, go[0].y, go[0].z, go[1].x));
+                    __stcs(dg + 1, make_float4(go[1].y, go[1].z, go[2].x, go[2].y));
+                    __stcs(dg + 2, make_float4(go[2].z, go[3].x, go[3].y, go[3].z));
+                } else if constexpr (PTS == 2) {
+                    __stcs(reinterpret_cast<float2 *>(ov + o_i), make_float2(best[0], best[1]));
+                    float2 *dg = reinterpret_cast<float2 *>(og + 3 * o_i);
+                    __stcs(dg, make_float2(go[0].x, go[0].y));
+                    __stcs(dg + 1, make_float2(go[0].z, go[1].x));
+                    __stcs(dg + 2, make_float2(go[1].y, go[1].z));
+                } else {
+                    ov[o_i] = best[0];
+                    og[3 * o_i] = go[0].x; og[3 * o_i + 1] = go[0].y; og[3 * o_i + 2] = go[0].z;
+                }
+            };
+            if constexpr (kMulti) {
+                for (int t = 0; t < tg.n; ++t) emit(tg.val[t], tg.grad[t]);
             } else {
-                out_val[o_i] = best[0];
-                out_grad[3 * o_i] = go[0].x; out_grad[3 * o_i + 1] = go[0].y; out_grad[3 * o_i + 2] = go[0].z;
-                if (out_which) out_which[o_i] = bs[0];
+                emit(out_val, out_grad);
+            }
+            if (out_which) {
+                if constexpr (PTS == 4) *reinterpret_cast<int4 *>(out_which + o_i) = make_int4(bs[0], bs[1], bs[2], bs[3]);
+                else if constexpr (PTS == 2) *reinterpret_cast<int2 *>(out_which + o_i) = make_int2(bs[0], bs[1]);
+                else out_which[o_i] = bs[0];
             }
         }
     }
@@ -812,10 +831,12 @@ struct __align__(16) CmSmem {
     int which[kCmCfg][kCmTilePts + 1];
 };
 
+template <bool kMulti>
 __global__ void __launch_bounds__(kCmCfg * kCmWarps, 3)
 composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_sdf, const float *__restrict__ xforms,
                          int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, long long n_pts,
-                         float *__restrict__ out_val, float *__restrict__ out_grad, int *__restrict__ out_which) {
+                         float *__restrict__ out_val, float *__restrict__ out_grad, int *__restrict__ out_which,
+                         const __grid_constant__ OutTargets tg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CmSmem &sm = *reinterpret_cast<CmSmem *>(smem_raw);
     NodeStage st; st.smem = nullptr; st.n = 0;
@@ -962,8 +983,15 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
             for (int r = warp; r < ncfg; r += kCmWarps) {
                 const float4 v = sm.out[r][lane];
                 const long long o_i = (long long)(c0 + r) * n_pts + pt;
-                __stcs(out_val + o_i, v.x);
-                __stcs(out_grad + 3 * o_i, v.y); __stcs(out_grad + 3 * o_i + 1, v.z); __stcs(out_grad + 3 * o_i + 2, v.w);
+                auto emit = [&](float *ov, float *og) {
+                    __stcs(ov + o_i, v.x);
+                    __stcs(og + 3 * o_i, v.y); __stcs(og + 3 * o_i + 1, v.z); __stcs(og + 3 * o_i + 2, v.w);
+                };
+                if constexpr (kMulti) {
+                    for (int t = 0; t < tg.n; ++t) emit(tg.val[t], tg.grad[t]);
+                } else {
+                    emit(out_val, out_grad);
+                }
                 if (out_which) out_which[o_i] = sm.which[r][lane];
             }
         }
@@ -1312,7 +1340,7 @@ extern "C" int pvb_sphere_query(float radius, const float *pts, int64_t n, float
 template <bool kMesh, int PTS, int MAXS>
 static int launch_composed(const pvb_sdf_desc *descs, int n_sdf, const float *xforms, int n_cfg, int cfg_begin,
                            int cfg_count, const float *pts, long long first_pt, long long n_pts, uint32_t mesh_mode,
-                           float *out_val, float *out_grad, int *out_which, cudaStream_t stream) {
+                           float *out_val, float *out_grad, int *out_which, const OutTargets *tg, cudaStream_t stream) {
     const long long n_items = (n_pts - first_pt) / PTS;
     if (n_items <= 0) return PVB_OK;
     DescPack<MAXS> pack;
@@ -1323,16 +1351,23 @@ static int launch_composed(const pvb_sdf_desc *descs, int n_sdf, const float *xf
     const long long cap = (long long)sm_count() * 64;     // bound the block count for huge configuration batches
     if ((long long)gx * gy > cap) { gy = (int)(cap / gx); if (gy < 1) gy = 1; }
     dim3 grid((unsigned)gx, (unsigned)gy);
-    composed_query_kernel<kMesh, PTS, MAXS><<<grid, kCompThreads, 0, stream>>>(
-        pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, first_pt, n_pts, mesh_mode, out_val, out_grad, out_which);
+    if (tg)
+        composed_query_kernel<kMesh, PTS, MAXS, true><<<grid, kCompThreads, 0, stream>>>(
+            pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, first_pt, n_pts, mesh_mode, nullptr, nullptr,
+            out_which, *tg);
+    else
+        composed_query_kernel<kMesh, PTS, MAXS, false><<<grid, kCompThreads, 0, stream>>>(
+            pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, first_pt, n_pts, mesh_mode, out_val, out_grad,
+            out_which, OutTargets{});
     PVB_CHECK_LAUNCH("pvb_composed_query");
     return PVB_OK;
 }
 
-extern "C" int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
-                                  int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count,
-                                  const float *pts, int64_t n_pts, uint32_t mesh_mode, float *out_val, float *out_grad,
-                                  int32_t *out_which, void *stream) {
+// tg == nullptr: one destination (out_val / out_grad); otherwise the kMulti instantiations store to every target
+static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
+                             int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count, const float *pts, int64_t n_pts,
+                             uint32_t mesh_mode, float *out_val, float *out_grad, int32_t *out_which,
+                             const OutTargets *tg, void *stream) {
     if (!descs || !xforms || n_sdf < 1 || n_cfg < 1 || cfg_begin < 0 || cfg_count < 0 ||
         cfg_begin + cfg_count > n_cfg || n_pts < 0 || (n_pts > 0 && cfg_count > 0 && (!pts || !out_val || !out_grad))) {
         pvb_set_error("pvb_composed_query: invalid argument (n_sdf=%d n_cfg=%d cfg=[%d,+%d) n_pts=%lld)", n_sdf, n_cfg,
@@ -1347,8 +1382,10 @@ extern "C" int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int3
     cudaStream_t s = (cudaStream_t)stream;
     auto aligned16 = [](const void *p) { return p == nullptr || ((uintptr_t)p % 16) == 0; };
     // 4-points-per-thread vector path needs 16-byte aligned rows: every configuration slab starts at c * n_pts
-    const bool vec = !needs_mesh && aligned16(pts) && aligned16(out_val) && aligned16(out_grad) &&
-                     aligned16(out_which) && (n_pts % 4 == 0);
+    bool out_aligned = aligned16(out_val) && aligned16(out_grad);
+    if (tg)
+        for (int t = 0; t < tg->n; ++t) out_aligned = out_aligned && aligned16(tg->val[t]) && aligned16(tg->grad[t]);
+    const bool vec = !needs_mesh && aligned16(pts) && out_aligned && aligned16(out_which) && (n_pts % 4 == 0);
     const long long n_vec = vec ? n_pts : 0;
     int rc = PVB_OK;
     static const int cfg_major = [] { const char *e = getenv("PVB_COMP_CFGMAJOR"); return e ? atoi(e) : 1; }();
@@ -1357,9 +1394,11 @@ extern "C" int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int3
     const int cm_tiles = (cfg_count + kCmCfg - 1) / kCmCfg;
     const bool cm_filled = cfg_count >= 16 && (double)cfg_count >= 0.85 * (double)(cm_tiles * kCmCfg);
     if (cfg_major && !needs_mesh && n_sdf <= kCmMaxS && cm_filled) {
-        static const bool smem_ok = cudaFuncSetAttribute(composed_cfgmajor_kernel,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int)sizeof(CmSmem)) == cudaSuccess;
+        static const bool smem_ok =
+            cudaFuncSetAttribute(composed_cfgmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(CmSmem)) == cudaSuccess &&
+            cudaFuncSetAttribute(composed_cfgmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(CmSmem)) == cudaSuccess;
         if (!smem_ok) {
             pvb_set_error("pvb_composed_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
             return PVB_ERR_CUDA;
@@ -1373,16 +1412,21 @@ extern "C" int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int3
         if (gx > n_tiles) gx = n_tiles;
         if (gx < 1) gx = 1;
         dim3 grid((unsigned)gx, (unsigned)gy);
-        composed_cfgmajor_kernel<<<grid, kCmCfg * kCmWarps, sizeof(CmSmem), s>>>(
-            pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, out_val, out_grad, out_which);
+        if (tg)
+            composed_cfgmajor_kernel<true><<<grid, kCmCfg * kCmWarps, sizeof(CmSmem), s>>>(
+                pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, nullptr, nullptr, out_which, *tg);
+        else
+            composed_cfgmajor_kernel<false><<<grid, kCmCfg * kCmWarps, sizeof(CmSmem), s>>>(
+                pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, out_val, out_grad, out_which,
+                OutTargets{});
         PVB_CHECK_LAUNCH("pvb_composed_query(cfg-major)");
         return PVB_OK;
     }
 #define PVB_COMP(MESH, PTS, FIRST, N)                                                                              \
     (n_sdf <= 16 ? launch_composed<MESH, PTS, 16>(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, FIRST, N,  \
-                                                  mesh_mode, out_val, out_grad, out_which, s)                      \
+                                                  mesh_mode, out_val, out_grad, out_which, tg, s)                  \
                  : launch_composed<MESH, PTS, 128>(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, FIRST, N, \
-                                                   mesh_mode, out_val, out_grad, out_which, s))
+                                                   mesh_mode, out_val, out_grad, out_which, tg, s))
     if (n_vec > 0) {
         rc = PVB_COMP(false, PVB_COMP_PTS, 0, n_pts);
     } else if (needs_mesh) {
@@ -1392,6 +1436,82 @@ extern "C" int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int3
     }
 #undef PVB_COMP
     return rc;
+}
+
+extern "C" int pvb_composed_query(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
+                                  int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count,
+                                  const float *pts, int64_t n_pts, uint32_t mesh_mode, float *out_val, float *out_grad,
+                                  int32_t *out_which, void *stream) {
+    return composed_dispatch(descs, n_sdf, needs_mesh, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, mesh_mode,
+                             out_val, out_grad, out_which, nullptr, stream);
+}
+
+extern "C" int pvb_composed_query_multi(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh,
+                                        const float *xforms, int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count,
+                                        const float *pts, int64_t n_pts, uint32_t mesh_mode,
+                                        const pvb_out_target *targets, int32_t n_targets, int32_t *out_which,
+                                        void *stream) {
+    if (!targets || n_targets < 1 || n_targets > PVB_MAX_TARGETS) {
+        pvb_set_error("pvb_composed_query_multi: n_targets must be 1..%d (got %d)", PVB_MAX_TARGETS, n_targets);
+        return PVB_ERR_INVALID;
+    }
+    OutTargets tg{};
+    tg.n = n_targets;
+    for (int t = 0; t < n_targets; ++t) {
+        if (!targets[t].val || !targets[t].grad) {
+            pvb_set_error("pvb_composed_query_multi: target %d has a null pointer", t);
+            return PVB_ERR_INVALID;
+        }
+        tg.val[t] = targets[t].val;
+        tg.grad[t] = targets[t].grad;
+    }
+    return composed_dispatch(descs, n_sdf, needs_mesh, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, mesh_mode,
+                             tg.val[0], tg.grad[0], out_which, &tg, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ peer buffers
+#define PVB_CUDA_TRY(call, what)                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            pvb_set_error("%s: %s", what, cudaGetErrorString(e_));                                   \
+            return PVB_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+extern "C" int pvb_ipc_alloc(int64_t bytes, void **out_ptr) {
+    if (bytes < 1 || !out_ptr) { pvb_set_error("pvb_ipc_alloc: invalid argument"); return PVB_ERR_INVALID; }
+    PVB_CUDA_TRY(cudaMalloc(out_ptr, (size_t)bytes), "pvb_ipc_alloc(cudaMalloc)");
+    return PVB_OK;
+}
+
+extern "C" int pvb_ipc_free(void *ptr) {
+    if (!ptr) return PVB_OK;
+    PVB_CUDA_TRY(cudaFree(ptr), "pvb_ipc_free(cudaFree)");
+    return PVB_OK;
+}
+
+extern "C" int pvb_ipc_export(void *ptr, unsigned char *handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == PVB_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!ptr || !handle) { pvb_set_error("pvb_ipc_export: invalid argument"); return PVB_ERR_INVALID; }
+    cudaIpcMemHandle_t h;
+    PVB_CUDA_TRY(cudaIpcGetMemHandle(&h, ptr), "pvb_ipc_export(cudaIpcGetMemHandle)");
+    memcpy(handle, &h, sizeof(h));
+    return PVB_OK;
+}
+
+extern "C" int pvb_ipc_open(const unsigned char *handle, void **out_ptr) {
+    if (!handle || !out_ptr) { pvb_set_error("pvb_ipc_open: invalid argument"); return PVB_ERR_INVALID; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    PVB_CUDA_TRY(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess), "pvb_ipc_open(cudaIpcOpenMemHandle)");
+    return PVB_OK;
+}
+
+extern "C" int pvb_ipc_close(void *ptr) {
+    if (!ptr) return PVB_OK;
+    PVB_CUDA_TRY(cudaIpcCloseMemHandle(ptr), "pvb_ipc_close(cudaIpcCloseMemHandle)");
+    return PVB_OK;
 }
 
 extern "C" int64_t pvb_chamfer_workspace(int64_t n_pts) {

@@ -9,7 +9,11 @@ sweeps when the caller wants the full result on every rank.
   sharded_query         ObjectFrameSDF over a shard of the flattened point axis (+ optional all-gather)
   sharded_robot_query   RobotSDF over a shard of the configuration batch (+ optional all-gather)
   sharded_chamfer       chamfer partial means over a shard of the cloud, all-reduced (B floats)
+  PeerResult            full-size RobotSDF result buffers mapped into every process of the node, so that
+                        sharded_robot_query(gather="peer") re-assembles the result with stores from the kernel
+                        epilogue (NVLink traffic under the lookups) instead of a trailing all-gather
 """
+import ctypes
 import math
 
 import torch
@@ -66,16 +70,109 @@ def sharded_query(sdf, points, gather=True, group=None):
     return val.reshape(lead), grad.reshape(*lead, 3)
 
 
-def sharded_robot_query(robot_sdf, points, gather=True, group=None):
+class _DeviceSpan:
+    """Raw device memory exposed through __cuda_array_interface__ so torch can view it without owning it."""
+
+    def __init__(self, address, n_float, owner):
+        self.owner = owner      # keeps the allocation alive as long as any tensor view exists
+        self.__cuda_array_interface__ = {"shape": (int(n_float),), "typestr": "<f4", "data": (int(address), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerResult:
+    """One full-size (n_cfg, n_pts) value / gradient buffer per rank, each mapped into every process of the node.
+
+    Rank r's RobotSDF kernel stores its configuration slab into all `world` buffers (its own and, over NVLink, the
+    peers'), so after `publish()` every rank holds the complete result -- the re-assembly SURVEY section 8(e) asks
+    for -- without a separate all-gather pass.  Buffers are plain cudaMalloc allocations shared with CUDA IPC
+    (pvb_ipc_*); same-node processes only, at most 8 ranks per launch (pvb.h PVB_MAX_TARGETS).
+    """
+
+    def __init__(self, n_cfg, n_pts, group=None):
+        from . import _native as nat
+        self.nat = nat
+        self.group = group
+        self.rank, self.world = _world(group)
+        if self.world > nat.MAX_TARGETS:
+            raise ValueError(f"PeerResult supports up to {nat.MAX_TARGETS} ranks, got {self.world}")
+        self.n_cfg, self.n_pts = int(n_cfg), int(n_pts)
+        n = self.n_cfg * self.n_pts
+        self._grad_offset = (4 * n + 255) // 256 * 256          # value block first, gradient block 256-B aligned
+        self.nbytes = self._grad_offset + 12 * n
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._peer_ptrs = {}
+        self._local = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().pvb_ipc_alloc(self.nbytes, ctypes.byref(self._local)), "pvb_ipc_alloc")
+            bases = [None] * self.world
+            bases[self.rank] = self._local.value
+            if self.world > 1:
+                handle = ctypes.create_string_buffer(nat.IPC_HANDLE_BYTES)
+                nat.check(nat.lib().pvb_ipc_export(self._local, handle), "pvb_ipc_export")
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    mapped = ctypes.c_void_p()
+                    nat.check(nat.lib().pvb_ipc_open(handles[r], ctypes.byref(mapped)), "pvb_ipc_open")
+                    self._peer_ptrs[r] = mapped.value
+                    bases[r] = mapped.value
+        self.val = torch.as_tensor(_DeviceSpan(bases[self.rank], n, self), device=self.device).view(self.n_cfg, self.n_pts)
+        self.grad = torch.as_tensor(_DeviceSpan(bases[self.rank] + self._grad_offset, 3 * n, self),
+                                    device=self.device).view(self.n_cfg, self.n_pts, 3)
+        # own buffer first, then the peers in ring order: at any moment the ranks target different destinations
+        order = [(self.rank + k) % self.world for k in range(self.world)]
+        self.targets = [(bases[r], bases[r] + self._grad_offset) for r in order]
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._closed = False
+
+    def publish(self):
+        """Stream-ordered barrier: when it completes on this rank, every rank's kernel (and with it all of its peer
+        stores) has finished, and no rank starts overwriting before everybody got here."""
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        """Unmap the peers' buffers and release the local one (collective: every rank must call it)."""
+        if self._closed:
+            return
+        self._closed = True
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for mapped in self._peer_ptrs.values():
+                self.nat.check(self.nat.lib().pvb_ipc_close(ctypes.c_void_p(mapped)), "pvb_ipc_close")
+            self._peer_ptrs = {}
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            self.val = self.grad = None
+            self.nat.check(self.nat.lib().pvb_ipc_free(self._local), "pvb_ipc_free")
+
+
+def sharded_robot_query(robot_sdf, points, gather=True, group=None, result=None):
     """RobotSDF over this rank's contiguous slab of the (flattened) configuration batch.
 
     The output slab (cfg_count, P) is a contiguous block of the (|A|, P) result, so re-assembly is a plain
-    concatenation on dim 0.  Returns ([A,] *B, N) / (..., 3) when gather=True, else the local slab and its range."""
+    concatenation on dim 0.  Returns ([A,] *B, N) / (..., 3) when gather=True, else the local slab and its range.
+    gather="peer" with a PeerResult: the kernel stores the slab into every rank's buffer directly (no all-gather);
+    the returned tensors are views of `result` and stay valid until the next query into it."""
     rank, world = _world(group)
     comp = robot_sdf.sdf
     n_cfg = 1 if comp.tsf_batch is None else math.prod(list(comp.tsf_batch))
     begin, end = shard_range(n_cfg, rank, world)
     P = points.reshape(-1, 3).shape[0]
+    if isinstance(gather, str):
+        if gather != "peer" or result is None:
+            raise ValueError('gather must be True, False or "peer" (the latter with result=PeerResult(...))')
+        if (result.n_cfg, result.n_pts) != (n_cfg, P):
+            raise ValueError(f"PeerResult is ({result.n_cfg}, {result.n_pts}), the query is ({n_cfg}, {P})")
+        comp.query_into(points, result.targets, cfg_begin=begin, cfg_count=end - begin)
+        result.publish()
+        lead = tuple(points.shape[:-1])
+        batch = tuple(comp.tsf_batch) if comp.tsf_batch is not None else ()
+        return result.val.view(*batch, *lead), result.grad.view(*batch, *lead, 3)
     val, grad = comp.query(points, cfg_begin=begin, cfg_count=end - begin)
     val = val.reshape(end - begin, P)
     grad = grad.reshape(end - begin, P, 3)

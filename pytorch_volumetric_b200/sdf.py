@@ -577,6 +577,38 @@ class ComposedSDF(ObjectFrameSDF):
                                                    nat.stream_ptr(device)), "pvb_composed_query")
         return (val, grad, which) if return_which else (val, grad)
 
+    def query_into(self, points_in_object_frame, targets, cfg_begin=0, cfg_count=None):
+        """`query` whose result slab is stored by the kernel epilogue into several full-size result buffers at once
+        (pvb_composed_query_multi): `targets` is a list of (val, grad) pairs, each a float32 tensor or a raw device
+        address of a buffer holding ALL n_cfg * P results -- typically this rank's buffer and the peer-mapped buffers
+        of the other ranks (distributed.PeerResult).  The slab lands at element cfg_begin * P of every buffer."""
+        S = len(self.sdfs)
+        n_cfg = 1 if self.tsf_batch is None else math.prod(list(self.tsf_batch))
+        if cfg_count is None:
+            cfg_count = n_cfg - cfg_begin
+        if not 1 <= len(targets) <= nat.MAX_TARGETS:
+            raise ValueError(f"between 1 and {nat.MAX_TARGETS} targets per launch, got {len(targets)}")
+        device = nat.compute_device(points_in_object_frame.device if torch.is_tensor(points_in_object_frame) else None)
+        with torch.cuda.device(device):
+            p = nat.as_f32_points(points_in_object_frame, device)
+            P = p.shape[0]
+            descs_arr, needs_mesh = self._native_descs(device)
+            if descs_arr is None:
+                raise NotImplementedError("query_into needs sub-SDFs with native descriptors (mesh / cached / sphere)")
+            arr = (nat.OutTarget * len(targets))()
+            for t, (tv, tg) in enumerate(targets):
+                for buf, per in ((tv, 1), (tg, 3)):
+                    if torch.is_tensor(buf) and (buf.dtype != torch.float32 or not buf.is_contiguous()
+                                                 or buf.numel() < per * n_cfg * P):
+                        raise ValueError("targets must be contiguous float32 buffers of the full (n_cfg * P) result")
+                arr[t].val = (tv.data_ptr() if torch.is_tensor(tv) else int(tv)) + 4 * cfg_begin * P
+                arr[t].grad = (tg.data_ptr() if torch.is_tensor(tg) else int(tg)) + 12 * cfg_begin * P
+            xf = self._xforms_on(device)
+            nat.check(nat.lib().pvb_composed_query_multi(descs_arr, S, int(needs_mesh), nat.ptr(xf), n_cfg, cfg_begin,
+                                                         cfg_count, nat.ptr(p), P, nat.PVB_MESH_DEFAULT,
+                                                         ctypes.cast(arr, ctypes.c_void_p), len(targets), None,
+                                                         nat.stream_ptr(device)), "pvb_composed_query_multi")
+
     def _generic_query(self, p, cfg_begin, cfg_count, n_cfg, return_which):
         """Sub-SDFs without a native descriptor (user subclasses, nested compositions): per-SDF evaluation through
         their own __call__, with the transform and the running min still on the GPU."""
