@@ -611,6 +611,7 @@ struct OutTargets {
     float *val[PVB_MAX_TARGETS];
     float *grad[PVB_MAX_TARGETS];
     int n;
+    int vec;        // all pointers 16-byte aligned and n_pts % 4 == 0: rows may be stored as float4
 };
 
 template <bool kMesh, int PTS, int MAXS, bool kMulti>
@@ -979,7 +980,31 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
         __syncthreads();
         // transposed store: one configuration row (32 consecutive points) per warp instruction
         const long long pt = tile * kCmTilePts + lane;
-        if (pt < n_pts) {
+        if (kMulti && tg.vec && tile * kCmTilePts + kCmTilePts <= n_pts) {
+            // Peer destinations are not cached on this side of NVLink, so every store instruction should leave as
+            // whole 32-byte sectors: a row is 128 B of values + 384 B of gradients, both contiguous -> lanes 0-7
+            // carry the values, lanes 8-31 the gradients, ONE 16-byte store per lane and destination (the strided
+            // 4-byte stores of the single-destination path measured 363 GB/s per rank on 8 GPUs).
+            for (int r = warp; r < ncfg; r += kCmWarps) {
+                const float *row = reinterpret_cast<const float *>(&sm.out[r][0]);     // {val, gx, gy, gz} per point
+                float w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = (lane < 8 ? lane : lane - 8) * 4 + j;       // element of the value / gradient row
+                    const int pp = lane < 8 ? e : e / 3;
+                    const int cc = lane < 8 ? 0 : 1 + (e - 3 * pp);
+                    w[j] = row[4 * pp + cc];
+                }
+                const float4 v4 = make_float4(w[0], w[1], w[2], w[3]);
+                const long long o_row = (long long)(c0 + r) * n_pts + tile * kCmTilePts;
+                for (int t = 0; t < tg.n; ++t) {
+                    float4 *dst = lane < 8 ? reinterpret_cast<float4 *>(tg.val[t] + o_row) + lane
+                                           : reinterpret_cast<float4 *>(tg.grad[t] + 3 * o_row) + (lane - 8);
+                    __stcs(dst, v4);
+                }
+                if (out_which) out_which[o_row + lane] = sm.which[r][lane];
+            }
+        } else if (pt < n_pts) {
             for (int r = warp; r < ncfg; r += kCmWarps) {
                 const float4 v = sm.out[r][lane];
                 const long long o_i = (long long)(c0 + r) * n_pts + pt;
@@ -1383,8 +1408,13 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
     auto aligned16 = [](const void *p) { return p == nullptr || ((uintptr_t)p % 16) == 0; };
     // 4-points-per-thread vector path needs 16-byte aligned rows: every configuration slab starts at c * n_pts
     bool out_aligned = aligned16(out_val) && aligned16(out_grad);
-    if (tg)
+    OutTargets tgv{};
+    if (tg) {
         for (int t = 0; t < tg->n; ++t) out_aligned = out_aligned && aligned16(tg->val[t]) && aligned16(tg->grad[t]);
+        tgv = *tg;
+        tgv.vec = out_aligned && (n_pts % 4 == 0);
+        tg = &tgv;
+    }
     const bool vec = !needs_mesh && aligned16(pts) && out_aligned && aligned16(out_which) && (n_pts % 4 == 0);
     const long long n_vec = vec ? n_pts : 0;
     int rc = PVB_OK;
@@ -1392,7 +1422,10 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
     // lanes = configurations: only worthwhile when the 32-wide configuration tiles are well filled (25 configurations
     // per rank on 8 GPUs would idle 22 % of the lanes; measured 0.176 ms against 0.111 ms point-major)
     const int cm_tiles = (cfg_count + kCmCfg - 1) / kCmCfg;
-    const bool cm_filled = cfg_count >= 16 && (double)cfg_count >= 0.85 * (double)(cm_tiles * kCmCfg);
+    // ... except with several destinations: the configuration-major epilogue owns whole rows and stores them as full
+    // sectors, which is what the NVLink-bound re-assembly needs; idle lanes cost less than partial-sector packets
+    const bool cm_filled = (cfg_count >= 16 && (double)cfg_count >= 0.85 * (double)(cm_tiles * kCmCfg)) ||
+                           (tg && tg->vec && cfg_count >= 8);
     if (cfg_major && !needs_mesh && n_sdf <= kCmMaxS && cm_filled) {
         static const bool smem_ok =
             cudaFuncSetAttribute(composed_cfgmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -24,7 +24,7 @@ def _arm(tmp_path, n_cfg):
     return s
 
 
-@pytest.mark.parametrize("n_cfg,n_pts", [(40, 4096), (5, 1001)])     # cfg-major kernel / point-major kernels
+@pytest.mark.parametrize("n_cfg,n_pts", [(40, 4096), (40, 4100), (5, 1001)])     # cfg-major (full-sector rows; ragged last tile) / point-major
 def test_multi_target_equals_single(tmp_path, n_cfg, n_pts):
     """Every destination of one multi-target launch holds exactly what the single-destination kernel writes, at the
     slab's place in the full buffer; elements outside the slab are untouched."""
