@@ -1,22 +1,24 @@
 """pytorch_volumetric_b200 -- B200-native (sm_100a) drop-in for pytorch_volumetric's batched SDF query path.
 
-Same public names as the reference's `pytorch_volumetric/__init__.py` for that path.
+The public names of the reference package (`pytorch_volumetric/__init__.py`) that belong to that path are
+re-exported here, so `import pytorch_volumetric_b200 as pv` reads like the original.
 """
-from .chamfer import batch_chamfer_dist, PlausibleDiversity, pairwise_distance, pairwise_distance_chamfer
-from .sdf import sample_mesh_points, ObjectFrameSDF, MeshSDF, CachedSDF, ComposedSDF, SDFQuery, \
-    ObjectFactory, MeshObjectFactory, OutOfBoundsStrategy, SphereSDF
-from .voxel import Voxels, VoxelGrid, VoxelSet, ExpandingVoxelGrid, get_divisible_range_by_resolution, \
-    get_coordinates_and_points_in_grid, voxel_down_sample
-from .model_to_sdf import RobotSDF, cache_link_sdf_factory, aabb_to_ordered_end_points
-from .transforms import Transform3d, Translate
-from .kinematics import build_serial_chain_from_urdf, SerialChain
-from . import distributed
+from . import chamfer as _chamfer, distributed, kinematics as _kin, model_to_sdf as _robot, sdf as _sdf, \
+    transforms as _tf, voxel as _voxel
 
-__all__ = [
-    "batch_chamfer_dist", "PlausibleDiversity", "pairwise_distance", "pairwise_distance_chamfer",
-    "sample_mesh_points", "ObjectFrameSDF", "MeshSDF", "CachedSDF", "ComposedSDF", "SDFQuery", "ObjectFactory",
-    "MeshObjectFactory", "OutOfBoundsStrategy", "SphereSDF", "Voxels", "VoxelGrid", "VoxelSet", "ExpandingVoxelGrid",
-    "voxel_down_sample", "get_divisible_range_by_resolution",
-    "get_coordinates_and_points_in_grid", "RobotSDF", "cache_link_sdf_factory", "aabb_to_ordered_end_points",
-    "Transform3d", "Translate", "build_serial_chain_from_urdf", "SerialChain", "distributed",
-]
+_EXPORTS = {
+    _sdf: ("CachedSDF", "ComposedSDF", "MeshObjectFactory", "MeshSDF", "ObjectFactory", "ObjectFrameSDF",
+           "OutOfBoundsStrategy", "SDFQuery", "SphereSDF", "sample_mesh_points"),
+    _robot: ("RobotSDF", "aabb_to_ordered_end_points", "cache_link_sdf_factory"),
+    _chamfer: ("PlausibleDiversity", "batch_chamfer_dist", "pairwise_distance", "pairwise_distance_chamfer"),
+    _voxel: ("ExpandingVoxelGrid", "VoxelGrid", "VoxelSet", "Voxels", "get_coordinates_and_points_in_grid",
+             "get_divisible_range_by_resolution", "voxel_down_sample"),
+    _tf: ("Transform3d", "Translate"),
+    _kin: ("SerialChain", "build_serial_chain_from_urdf"),
+}
+for _module, _names in _EXPORTS.items():
+    for _name in _names:
+        globals()[_name] = getattr(_module, _name)
+
+__all__ = sorted(n for names in _EXPORTS.values() for n in names) + ["distributed"]
+del _module, _names, _name

@@ -8,8 +8,6 @@ path and its callers use (`raw_data`, `shape`, `ensure_index_key`,
 `ravel_multi_index`, `get_valid_values`, `ensure_value_key`, `view[pts]`).
 """
 import abc
-import copy
-import math
 
 import numpy as np
 import torch
@@ -100,50 +98,63 @@ class GridView:
 
 
 class Voxels(abc.ABC):
-    """Interface of the voxel containers (reference voxel.py:28-39)."""
+    """What every voxel container offers (reference voxel.py:28-39): read, write, and list what is stored."""
 
     @abc.abstractmethod
     def get_known_pos_and_values(self):
-        """positions (N x d) and values (N) of the voxels that hold something"""
+        """(N x d positions, N values) of the voxels that hold something."""
 
     @abc.abstractmethod
     def __getitem__(self, pts):
-        """values (N) at positions (N x d)"""
+        """Values (N) stored at positions (N x d)."""
 
     @abc.abstractmethod
     def __setitem__(self, pts, value):
-        """store values (N) at positions (N x d)"""
+        """Store values (N) at positions (N x d)."""
+
+
+def _extent(points):
+    """Per-axis (min, max) of an N x d tensor as two numpy vectors."""
+    return points.min(dim=0).values.cpu().numpy(), points.max(dim=0).values.cpu().numpy()
 
 
 class VoxelGrid(Voxels):
-    """Dense voxel container over a snapped range (reference voxel.py:42-91); used as the default
-    lattice of ObjectFrameSDF.get_voxel_view."""
+    """Dense container over a range snapped to whole cells (reference voxel.py:42-91); also the default lattice of
+    ObjectFrameSDF.get_voxel_view.  Cells holding `invalid_val` (0) count as empty."""
+
+    invalid_val = 0
 
     def __init__(self, resolution, range_per_dim, dtype=torch.float, device='cpu'):
-        self.resolution = resolution
-        self.invalid_val = 0
-        self.dtype = dtype
-        self.device = device
-        self._create_voxels(resolution, range_per_dim)
+        self.resolution, self.dtype, self.device = resolution, dtype, device
+        self._rebuild(range_per_dim)
+
+    def _rebuild(self, box):
+        """Allocate an empty grid over `box` (snapped); the previous contents are dropped."""
+        snapped = get_divisible_range_by_resolution(self.resolution, box)
+        self.coords, self.pts = get_coordinates_and_points_in_grid(self.resolution, snapped, device=self.device)
+        self._data = torch.zeros(tuple(len(axis) for axis in self.coords), dtype=self.dtype, device=self.device)
+        self.voxels = GridView(self._data, snapped, invalid_value=self.invalid_val)
+        self.range_per_dim = np.array(snapped)
 
     def _create_voxels(self, resolution, range_per_dim):
-        self.range_per_dim = get_divisible_range_by_resolution(resolution, range_per_dim)
-        self.coords, self.pts = get_coordinates_and_points_in_grid(resolution, self.range_per_dim, device=self.device)
-        self._data = torch.zeros([len(c) for c in self.coords], dtype=self.dtype, device=self.device)
-        self.voxels = GridView(self._data, self.range_per_dim, invalid_value=self.invalid_val)
-        self.range_per_dim = np.array(self.range_per_dim)
+        """The reference's name for re-creating the grid (voxel.py:50)."""
+        self.resolution = resolution
+        self._rebuild(range_per_dim)
+
+    def _regrid(self, box):
+        """Move the stored voxels to a new grid over `box`."""
+        pos, val = self.get_known_pos_and_values()
+        self._rebuild(box)
+        if pos.numel():
+            self.voxels[pos] = val
 
     def resize_to_fit(self):
-        """Shrink / move the grid so that it just contains the known voxels (one cell of slack per side)."""
-        pos, val = self.get_known_pos_and_values()
+        """Tighten the range around the stored voxels, one cell of slack on every side."""
+        pos, _ = self.get_known_pos_and_values()
         if pos.numel() == 0:
             return
-        lo, hi = pos.min(dim=0).values, pos.max(dim=0).values
-        box = copy.deepcopy(self.range_per_dim)
-        for d in range(len(lo)):
-            box[d] = (lo[d].item() - self.resolution, hi[d].item() + self.resolution)
-        self._create_voxels(self.resolution, box)
-        self.__setitem__(pos, val)
+        lo, hi = _extent(pos)
+        self._regrid(np.stack((lo - self.resolution, hi + self.resolution), axis=1))
 
     def get_voxel_center_points(self):
         return self.pts
@@ -152,10 +163,10 @@ class VoxelGrid(Voxels):
         return self._data
 
     def get_known_pos_and_values(self):
-        known = self.voxels.raw_data != self.invalid_val
-        idx = known.nonzero()
-        unravel = torch.stack(torch.unravel_index(idx.reshape(-1), tuple(self.voxels.shape)), dim=-1)
-        return self.voxels.ensure_value_key(unravel), self.voxels.raw_data[idx.reshape(-1)]
+        flat = self.voxels.raw_data
+        filled = (flat != self.invalid_val).nonzero().reshape(-1)
+        cells = torch.stack(torch.unravel_index(filled, tuple(self.voxels.shape)), dim=-1)
+        return self.voxels.ensure_value_key(cells), flat[filled]
 
     def __getitem__(self, pts):
         return self.voxels[pts]
@@ -165,38 +176,35 @@ class VoxelGrid(Voxels):
 
 
 class ExpandingVoxelGrid(VoxelGrid):
-    """VoxelGrid whose range grows, in whole cells, whenever a write falls outside it (reference voxel.py:94-117)."""
+    """VoxelGrid that grows, by whole cells, to cover whatever is written to it (reference voxel.py:94-117)."""
 
     def __setitem__(self, pts, value):
         if pts.numel() > 0:
-            lo, hi = pts.min(dim=0).values, pts.max(dim=0).values
-            box = copy.deepcopy(self.range_per_dim)
-            for d in range(len(lo)):
-                above = (hi[d] - self.range_per_dim[d][1]).item()
-                below = (self.range_per_dim[d][0] - lo[d]).item()
-                if above > 0:
-                    box[d][1] += math.ceil(above / self.resolution) * self.resolution
-                if below > 0:
-                    box[d][0] -= math.ceil(below / self.resolution) * self.resolution
-            if not np.allclose(box, self.range_per_dim):
-                pos, val = self.get_known_pos_and_values()      # carry the contents over to the larger grid
-                self._create_voxels(self.resolution, box)
-                super().__setitem__(pos, val)
-        return super().__setitem__(pts, value)
+            # overshoot per axis in the points' own precision, like the reference's tensor - scalar arithmetic
+            box = torch.as_tensor(self.range_per_dim, dtype=pts.dtype, device=pts.device)
+            under = (box[:, 0] - pts.min(dim=0).values).double().cpu().numpy()
+            over = (pts.max(dim=0).values - box[:, 1]).double().cpu().numpy()
+            cells_below = np.ceil(np.clip(under, 0, None) / self.resolution)
+            cells_above = np.ceil(np.clip(over, 0, None) / self.resolution)
+            if cells_below.any() or cells_above.any():
+                grown = self.range_per_dim + np.stack((-cells_below, cells_above), axis=1) * self.resolution
+                if not np.allclose(grown, self.range_per_dim):
+                    self._regrid(grown)         # the contents move to the larger grid first
+        super().__setitem__(pts, value)
 
 
 class VoxelSet(Voxels):
-    """Explicit list of occupied positions and their values (reference voxel.py:120-134)."""
+    """Sparse container: an explicit list of positions with their values (reference voxel.py:120-134)."""
 
     def __init__(self, positions, values):
-        self.positions = positions
-        self.values = values
+        self.positions, self.values = positions, values
 
     def __getitem__(self, pts):
         raise RuntimeError("Cannot get arbitrary points on a voxel set")
 
     def __setitem__(self, pts, value):
-        self.positions = torch.cat((self.positions, pts.view(-1, self.positions.shape[-1])), dim=0)
+        width = self.positions.shape[-1]
+        self.positions = torch.cat((self.positions, pts.view(-1, width)), dim=0)
         self.values = torch.cat((self.values, value))
 
     def get_known_pos_and_values(self):
@@ -204,29 +212,29 @@ class VoxelSet(Voxels):
 
 
 def bounds_contain_another_bounds(outer_bounds, inner_bounds):
-    outer_bounds, inner_bounds = np.asarray(outer_bounds), np.asarray(inner_bounds)
-    return bool(np.all(outer_bounds[:, 0] <= inner_bounds[:, 0]) and np.all(outer_bounds[:, 1] >= inner_bounds[:, 1]))
+    outer, inner = np.asarray(outer_bounds), np.asarray(inner_bounds)
+    return bool((outer[:, 0] <= inner[:, 0]).all() and (outer[:, 1] >= inner[:, 1]).all())
 
 
 def voxel_down_sample(points, resolution, range_per_dim=None, ignore_flat_dim=False):
-    """Down-sample an N x D cloud to the centres of the occupied cells of a grid of the given resolution
-    (reference voxel.py:141-171): all points are scattered into a boolean grid at once, the occupied cells are
-    read back.  Runs on the device the points live on."""
+    """One point per occupied cell of a grid of the given resolution: the cell centre (reference voxel.py:141-171).
+    The whole N x D cloud is scattered into a boolean grid in one indexed write and the set cells are read back;
+    runs on the device the points live on."""
     if points.shape[0] == 0:
         return points
-    data_bounds = np.stack((points.min(dim=0)[0].cpu().numpy() - resolution * 2,
-                            points.max(dim=0)[0].cpu().numpy() + resolution * 2)).T
-    if range_per_dim is None or bounds_contain_another_bounds(range_per_dim, data_bounds):
-        range_per_dim = data_bounds
-    flat_z = ignore_flat_dim and range_per_dim[-1][0] == range_per_dim[-1][1]
-    flat_z_val = range_per_dim[-1][0]
-    if flat_z:
-        range_per_dim = range_per_dim[:-1]
-        points = points[..., :-1]
-    grid = VoxelGrid(resolution, range_per_dim, device=points.device, dtype=torch.bool)
-    grid[points] = 1
-    pts, _ = grid.get_known_pos_and_values()
-    pts = pts.to(points.dtype)
-    if flat_z:
-        pts = torch.cat((pts, torch.ones((pts.shape[0], 1), device=points.device, dtype=pts.dtype) * flat_z_val), dim=-1)
-    return pts
+    lo, hi = _extent(points)
+    margin = 2 * resolution
+    cloud_box = np.stack((lo - margin, hi + margin), axis=1)
+    # a caller-supplied range is only honoured when it does NOT already enclose the data (reference voxel.py:153-154)
+    box = cloud_box if range_per_dim is None or bounds_contain_another_bounds(range_per_dim, cloud_box) \
+        else range_per_dim
+    drop_last = bool(ignore_flat_dim and box[-1][0] == box[-1][1])
+    if drop_last:
+        flat_coordinate = box[-1][0]
+        box, points = box[:-1], points[..., :-1]
+    occupancy = VoxelGrid(resolution, box, device=points.device, dtype=torch.bool)
+    occupancy[points] = 1
+    centres = occupancy.get_known_pos_and_values()[0].to(points.dtype)
+    if drop_last:
+        centres = torch.nn.functional.pad(centres, (0, 1), value=float(flat_coordinate))
+    return centres
