@@ -83,76 +83,9 @@ __device__ __forceinline__ float box_d2(float lx, float ly, float lz, float hx, 
 // order, 11.3 ms against 9.9 ms for testing leaves inline -- the extra local-memory stack traffic costs more than
 // the better lane occupancy of the triangle code buys; runs of consecutive queries seeded with the previous closest
 // point, 11.4-15.9 ms.)
-#ifndef PVB_CLOSEST_WHILE_WHILE
-// 1: phase-aligned "while-while" walk.  Measured against the inline-leaf walk below (ms, mesh10k / C5 / C3):
-// 7.6 / 7.7 / 13.9 against 7.6 / 7.6 / 13.1 -- no gain: the cost is in the triangle tests themselves.
-#define PVB_CLOSEST_WHILE_WHILE 0
-#endif
-#if PVB_CLOSEST_WHILE_WHILE
-// while-while variant (Aila & Laine): every lane first advances its walk until it holds a leaf, then all lanes that
-// hold one test its triangles together.  Leaves travel through the stack like inner nodes.
-__device__ __forceinline__ Closest bvh_closest(const float4 *__restrict__ gnodes, const NodeStage &st,
-                                               const float4 *__restrict__ tris, f3 p, float init_d2) {
-    Closest best;
-    best.q = mk3(0.f, 0.f, 0.f);
-    best.d2 = init_d2;
-    best.face = -1;
-    int stack_n[kStack];
-    float stack_d[kStack];
-    int sp = 0;
-    stack_n[sp] = 0; stack_d[sp] = 0.f; ++sp;
-    constexpr float kSlack = 0.99999f;
-    for (;;) {
-        int leaf = 0;
-        bool has_leaf = false;
-        while (sp > 0 && !has_leaf) {
-            --sp;
-            const int ref = stack_n[sp];
-            if (stack_d[sp] * kSlack > best.d2) continue;
-            if (ref < 0) { leaf = ref; has_leaf = true; break; }
-            const float4 *n = node_ptr(gnodes, st, ref);
-            const float4 lox = n[0], loy = n[1], loz = n[2], hix = n[3], hiy = n[4], hiz = n[5];
-            const int4 ch = *reinterpret_cast<const int4 *>(n + 6);
-            float d[4];
-            int c[4];
-            d[0] = box_d2(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, p); c[0] = ch.x;
-            d[1] = box_d2(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, p); c[1] = ch.y;
-            d[2] = box_d2(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, p); c[2] = ch.z;
-            d[3] = box_d2(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, p); c[3] = ch.w;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (c[k] == INT32_MIN) d[k] = PVB_INF;
-#define PVB_CSWAP(i, j)                                                          \
-    if (d[j] < d[i]) { const float td = d[i]; d[i] = d[j]; d[j] = td;            \
-                       const int tc = c[i]; c[i] = c[j]; c[j] = tc; }
-            PVB_CSWAP(0, 1) PVB_CSWAP(2, 3) PVB_CSWAP(0, 2) PVB_CSWAP(1, 3) PVB_CSWAP(1, 2)
-#undef PVB_CSWAP
-#pragma unroll
-            for (int k = 3; k >= 0; --k) {
-                if (c[k] != INT32_MIN && d[k] * kSlack <= best.d2 && sp < kStack) {
-                    stack_n[sp] = c[k]; stack_d[sp] = d[k]; ++sp;
-                }
-            }
-        }
-        if (!has_leaf) break;
-        const unsigned code = (unsigned)~leaf;
-        const int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
-        for (int t = first; t < first + cnt; ++t) {
-            const float4 v0 = __ldg(tris + 3 * (size_t)t);
-            const float4 v1 = __ldg(tris + 3 * (size_t)t + 1);
-            const float4 v2 = __ldg(tris + 3 * (size_t)t + 2);
-            const f3 q = closest_on_triangle(p, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z));
-            const f3 g = q - p;
-            const float dd = dot(g, g);
-            const int face = __float_as_int(v0.w);
-            if (dd < best.d2 || (dd == best.d2 && (best.face < 0 || face < best.face))) {
-                best.d2 = dd; best.q = q; best.face = face;
-            }
-        }
-    }
-    return best;
-}
-#else
+// A phase-aligned "while-while" walk (Aila & Laine: advance to a leaf first, then test triangles together) was also
+// measured: mesh10k / C5 / C3 7.6 / 7.7 / 13.9 ms against 7.6 / 7.6 / 13.1 ms for this inline-leaf walk -- no gain,
+// the cost is in the triangle tests themselves; see profiles/README.md.
 __device__ __forceinline__ Closest bvh_closest(const float4 *__restrict__ gnodes, const NodeStage &st,
                                                const float4 *__restrict__ tris, f3 p, float init_d2) {
     Closest best;
@@ -219,8 +152,6 @@ __device__ __forceinline__ Closest bvh_closest(const float4 *__restrict__ gnodes
     }
     return best;
 }
-
-#endif
 
 // ----------------------------------------------------------------------------
 // Crossing parity of the ray o + t*dir, t in [0, inf), with the triangle soup.

@@ -571,12 +571,6 @@ constexpr int kCompSmemXf = 64;
 #ifndef PVB_COMPMESH_MINB
 #define PVB_COMPMESH_MINB 4   // C3 (16 drills): 16.4 / 14.6 / 13.1 ms at 1 / 3 / 4 CTAs per SM
 #endif
-#ifndef PVB_COMP_BESTFIRST
-// 1: evaluate the sub-SDF with the smallest AABB lower bound first (an extra pass over the transforms).  Measured
-// on C4 (profiles/README.md): fewer table gathers but 1.8x slower -- the kernel is instruction-issue bound, the
-// extra pass costs more than the gathers it saves.  Kept for reference.
-#define PVB_COMP_BESTFIRST 0
-#endif
 
 // `order` is the sequence in which the sub-SDFs are visited: the bit-reversal permutation of 0..n-1.  Along a
 // kinematic chain the distance to consecutive links changes monotonically for most points, so index order makes
@@ -706,40 +700,9 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
                 }
             };
 
-            // pass 1 (no table access): the sub-SDF with the smallest AABB lower bound is evaluated first so that
-            // the running min is tight before anything else is considered
-            int first[PTS];
-            if (PVB_COMP_BESTFIRST && n_sdf > 1) {
-                float lbmin[PTS];
-#pragma unroll
-                for (int k = 0; k < PTS; ++k) { lbmin[k] = PVB_INF; first[k] = 0; }
-                for (int s = 0; s < n_sdf; ++s) {
-                    float4 r0, r1, r2;
-                    load_xf(s, r0, r1, r2);
-#pragma unroll
-                    for (int k = 0; k < PTS; ++k) {
-                        const float lb2 = aabb_lb2(descs.d[s], xform(r0, r1, r2, p[k]));
-                        if (lb2 < lbmin[k]) { lbmin[k] = lb2; first[k] = s; }
-                    }
-                }
-                // evaluate each point's first choice; the loop keeps the descriptor index warp-uniform
-                // (constant-bank reads with a per-lane index would be replayed per distinct value)
-                for (int s = 0; s < n_sdf; ++s) {
-                    bool any = false;
-#pragma unroll
-                    for (int k = 0; k < PTS; ++k) any |= (first[k] == s);
-                    if (!any) continue;
-                    float4 r0, r1, r2;
-                    load_xf(s, r0, r1, r2);
-#pragma unroll
-                    for (int k = 0; k < PTS; ++k)
-                        if (first[k] == s) evaluate(descs.d[s], s, k, xform(r0, r1, r2, p[k]));
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < PTS; ++k) first[k] = -1;
-            }
-            // pass 2: everything else, skipped when provably not the argmin
+            // (Evaluating the sub-SDF with the smallest AABB lower bound first -- an extra pass over all of them without
+            // table access -- saves lookups but measured 1.8x slower: the kernel is issue-bound; profiles/README.md.)
+            // every sub-SDF in visiting order, skipped when provably not the argmin
             for (int si = 0; si < n_sdf; ++si) {
                 const int s = descs.order[si];
                 const pvb_sdf_desc &d = descs.d[s];
@@ -748,7 +711,6 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
                 const bool prunable = d.kind == PVB_KIND_GRID && (d.flags & PVB_GRID_PRUNE_OK);
 #pragma unroll
                 for (int k = 0; k < PTS; ++k) {
-                    if (s == first[k]) continue;
                     const f3 q = xform(r0, r1, r2, p[k]);
                     if (prunable && bs[k] >= 0) {
                         // value >= dist(q, AABB) - margin: skip when that bound already exceeds the running min
@@ -815,11 +777,8 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
 // the point.  Results are bit-identical to the point-major kernel (same transform / lookup arithmetic; pruning is
 // exact).  A block owns a tile of 32 configurations x 32 points; results are transposed through shared memory so
 // that global stores stay coalesced along the point axis.
-#ifndef PVB_CM_BESTFIRST
-// 1: visit the link with the nearest bounding sphere first.  Measured (C4 / README shape): 1.26 / 0.224 ms against
-// 1.05 / 0.182 ms for plain index order -- like PVB_COMP_BESTFIRST, the extra pass costs more than the lookups it saves.
-#define PVB_CM_BESTFIRST 0
-#endif
+// (Visiting the link with the nearest bounding sphere first was measured on C4 / the README shape: 1.26 / 0.224 ms
+// against 1.05 / 0.182 ms in index order -- the extra pass costs more than the lookups it saves.)
 constexpr int kCmCfg = 32;
 constexpr int kCmWarps = 8;
 constexpr int kCmPts = 4;                         // points per thread
@@ -921,34 +880,6 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
                 }
             }
         };
-        // pass 0 (no table access, no transform): the link whose bounding sphere is nearest goes first, so that the
-        // running min is already tight when the others are considered (PVB_CM_BESTFIRST)
-        int first[kCmPts];
-#pragma unroll
-        for (int k = 0; k < kCmPts; ++k) first[k] = -1;
-        if (PVB_CM_BESTFIRST && n_sdf > 1) {
-            float lbmin[kCmPts];
-#pragma unroll
-            for (int k = 0; k < kCmPts; ++k) { lbmin[k] = PVB_INF; first[k] = 0; }
-            for (int s = 0; s < n_sdf; ++s) {
-                const float4 sp = sm.sph[lane][s];
-                const float rad = sp.w < PVB_INF ? sp.w : 0.f;
-#pragma unroll
-                for (int k = 0; k < kCmPts; ++k) {
-                    const float dx = p[k].x - sp.x, dy = p[k].y - sp.y, dz = p[k].z - sp.z;
-                    // ordering key only (not a bound): squared centre distance minus squared radius
-                    const float key = dx * dx + dy * dy + dz * dz - rad * rad;
-                    if (key < lbmin[k]) { lbmin[k] = key; first[k] = s; }
-                }
-            }
-            for (int s = 0; s < n_sdf; ++s) {          // descriptor index stays warp-uniform
-                bool need[kCmPts];
-                bool any = false;
-#pragma unroll
-                for (int k = 0; k < kCmPts; ++k) { need[k] = pon[k] && first[k] == s; any |= need[k]; }
-                if (any) visit(s, need);
-            }
-        }
         for (int si = 0; si < n_sdf; ++si) {
             const int s = descs.order[si];
             const float4 sp = sm.sph[lane][s];
@@ -961,7 +892,7 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
                 const float dx = p[k].x - sp.x, dy = p[k].y - sp.y, dz = p[k].z - sp.z;
                 const float d2 = dx * dx + dy * dy + dz * dz;
                 const bool pruned = bs[k] >= 0 && (thr < 0.f || d2 * 0.9998f > thr * thr);
-                need[k] = pon[k] && !pruned && first[k] != s;
+                need[k] = pon[k] && !pruned;
                 any |= need[k];
             }
             if (any) visit(s, need);
