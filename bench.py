@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- SDF+grad queries/s of the batched signed-distance query path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|mesh10k|c3|c4|c5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W]
+                    [--workload c2|mesh10k|mesh50k|c3|c3cached|c4|c4gather|c4peer|c4readme|c5] [--impl reference]
 
 One "step" = one pass of the hot path over one batch of synthetic input.  The default workload is BASELINE.json
 configs[1] (C2): CachedSDF(res=0.005) of the YCB drill, 10^7 random query points (42 % out of range), value +
@@ -435,40 +436,145 @@ def make_workload(name, rank, world):
 
 
 # ------------------------------------------------------------------------------------------- reference arm
+class CpuArm:
+    """One workload on the host through the oracle port.  `run(n)` evaluates the first n sample points (n <= max_n);
+    one point is `units_per_point` units of the metric (the number of configurations for RobotSDF)."""
+
+    def __init__(self, run, max_n, what, label, units_per_point=1):
+        self.run, self.max_n, self.what, self.label, self.units_per_point = run, max_n, what, label, units_per_point
+
+
+def cpu_arm(name):
+    """CPU implementation of one workload from the oracle port (never touches the GPU).  Tables the GPU arm builds
+    on the device are rebuilt on the host with the oracle's OpenMP BVH evaluator, untimed."""
+    from oracle import port, tp_open3d
+    from oracle import tp_pytorch_kinematics as opk
+    tp_open3d.QUERY_METHOD = "bvh"
+    np.random.seed(0)
+    if name == "c2":
+        v, f = workloads.fixture_mesh("drill")
+        mesh = port.MeshPort(vertices=v, faces=f, name="drill")
+        sdf = port.CachedSDFPort("drill", 0.005, mesh.bounding_box(padding=0.1), port.MeshSDFPort(mesh))
+        lo = np.array([r[0] for r in sdf.ranges]); hi = np.array([r[1] for r in sdf.ranges])
+        max_n = 2_000_000
+        pts = workloads.uniform_points(max_n, lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo), seed=0)
+        return CpuArm(lambda n: sdf(pts[:n]), max_n,
+                      "oracle/port.py CachedSDFPort (op-for-op torch-cpu restatement of sdf.py:535-571)",
+                      "C2 CachedSDF(drill, res=0.005) value+gradient")
+    if name in ("mesh10k", "mesh50k"):
+        v, f = workloads.bumpy_sphere(*((100, 51) if name == "mesh10k" else (250, 101)))
+        mesh = port.MeshPort(vertices=v, faces=f)
+        max_n = 400_000
+        pts = workloads.uniform_points(max_n, v.min(0) - 0.05, v.max(0) + 0.05, seed=2)
+        return CpuArm(lambda n: mesh.closest_point(pts[:n]), max_n,
+                      "oracle MeshPort.closest_point over the OpenMP BVH evaluator (sdf.py:122-172 restated)",
+                      f"MeshSDF on {len(f)}-triangle bumpy sphere")
+    if name in ("c3", "c3cached"):
+        v, f = workloads.fixture_mesh("drill")
+        mesh = port.MeshPort(vertices=v, faces=f, name="drill")
+        sub = port.MeshSDFPort(mesh)
+        if name == "c3cached":
+            sub = port.CachedSDFPort("drill", 0.005, mesh.bounding_box(padding=0.1), sub)
+        comp = port.ComposedSDFPort([sub] * 16, opk.Transform3d(matrix=workloads.random_rigid(16, seed=1, t_range=0.5)))
+        max_n = 200_000 if name == "c3cached" else 50_000
+        pts = workloads.uniform_points(max_n, [-0.7] * 3, [0.7] * 3, seed=3)
+        return CpuArm(lambda n: comp(pts[:n]), max_n,
+                      "uniform points of the [-0.7, 0.7]^3 query box x 16 sub-SDFs; oracle/port.py ComposedSDFPort "
+                      "(sdf.py:392-433 restated: per-SDF loop + argmin)",
+                      f"C3 ComposedSDF of 16 drills ({'CachedSDF res=0.005' if name == 'c3cached' else 'MeshSDF'})")
+    if name in ("c4", "c4gather", "c4peer", "c4readme"):
+        d = os.path.join(tempfile.gettempdir(), "pvb_bench_arm_cpu")
+        urdf, end = workloads.write_arm(d)
+        chain = opk.build_serial_chain_from_urdf(open(urdf).read(), end)
+        robot = port.RobotSDFPort(chain, path_prefix=d, link_sdf_factory=port.cache_link_sdf_factory_port(0.02, 1.0))
+        n_cfg, max_n = 20, 50_000
+        robot.set_joint_configuration(workloads.arm_configurations(n_cfg))
+        lo = [r[0] for r in workloads.ARM_QUERY_RANGE]; hi = [r[1] for r in workloads.ARM_QUERY_RANGE]
+        pts = workloads.uniform_points(max_n, lo, hi, seed=4)
+        return CpuArm(lambda n: robot(pts[:n]), max_n,
+                      f"{n_cfg} of the 200 configurations per point (8 links each); oracle/port.py RobotSDFPort "
+                      f"(model_to_sdf.py:82-125 + sdf.py:392-433 restated)",
+                      "C4 RobotSDF synthetic 7-DOF arm (8 links, CachedSDF res=0.02 pad=1.0)", units_per_point=n_cfg)
+    if name == "c5":
+        v, f = workloads.bumpy_sphere(250, 101)
+        mesh = port.MeshPort(vertices=v, faces=f)
+        max_n = 1_000_000
+        g = torch.Generator().manual_seed(5)
+        idx = torch.randint(0, len(v), (max_n,), generator=g)
+        tf = workloads.random_rigid(1, seed=5, t_range=0.1)[0]
+        surf = torch.from_numpy(np.asarray(v, dtype=np.float32))[idx]
+        cloud = surf @ tf[:3, :3].T + tf[:3, 3] + 0.002 * torch.randn(max_n, 3, generator=g)
+        w2o = torch.linalg.inv(tf.unsqueeze(0))
+        return CpuArm(lambda n: port.batch_chamfer_dist_port(w2o, cloud[:n], mesh=mesh), max_n,
+                      "cloud points, B=1; oracle/port.py batch_chamfer_dist_port (chamfer.py:79-94 restated, OpenMP "
+                      "BVH closest point)", "C5 chamfer: point cloud -> 50 000-triangle bumpy sphere")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def usable_cpus():
+    """CPUs this process may actually run on: affinity mask, capped by the cgroup CPU quota when there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:                                            # cgroup v2
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(quota) // int(period)))
+    except (OSError, ValueError):
+        pass
+    try:                                            # cgroup v1
+        quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if quota > 0:
+            n = min(n, max(1, quota // period))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def pick_cpu_threads(probe):
+    """Run the CPU arm with the thread count that is FASTEST on this host.  `probe()` is a small slice of the
+    workload.  Asking torch-cpu / OpenMP for every core the OS reports is not always that: the masked-index ops of
+    the reference path are memory bound and a 128-thread launch of each of them read 35x slower than 8 threads on a
+    2 M-point sample (first bench lines of this round), which would flatter the GPU arm.  Returns (threads, tried)."""
+    from oracle import _geom
+    top = usable_cpus()
+    tried = {}
+    probe()                                         # first-touch / lazy-initialisation cost stays out of the comparison
+    for c in sorted({top, max(1, top // 2), 32, 16, 8, 4}, reverse=True):
+        if c > top:
+            continue
+        torch.set_num_threads(c)
+        _geom.set_num_threads(c)
+        t0 = time.perf_counter()
+        probe()
+        tried[c] = time.perf_counter() - t0
+    best = min(tried, key=tried.get)
+    torch.set_num_threads(best)
+    _geom.set_num_threads(best)
+    return best, tried
+
+
+REFERENCE_ARM_BUDGET_S = 150.0      # the whole --impl reference run (warm-up + timed steps) is sized to about this
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    if args.workload not in ("c2", "mesh10k", "mesh50k"):
-        print(json.dumps({"impl": "reference", "unavailable": f"CPU arm implemented for c2 / mesh10k, not {args.workload}"}))
-        return 0
-    # The CPU arm needs the same tables as the GPU arm.  They are rebuilt on the host with the oracle's BVH
-    # evaluator (no GPU involvement), untimed.
-    from oracle import port, tp_open3d, _geom
-    torch.set_num_threads(os.cpu_count() or 1)
-    cores = max(torch.get_num_threads(), _geom.num_threads())
-    if args.workload == "c2":
-        tp_open3d.QUERY_METHOD = "bvh"
-        v, f = workloads.fixture_mesh("drill")
-        mesh = port.MeshPort(vertices=v, faces=f, name="drill")
-        np.random.seed(0)
-        sdf = port.CachedSDFPort("drill", 0.005, mesh.bounding_box(padding=0.1), port.MeshSDFPort(mesh))
-        lo = np.array([r[0] for r in sdf.ranges]); hi = np.array([r[1] for r in sdf.ranges])
-        sample = 2_000_000
-        pts = workloads.uniform_points(sample, lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo), seed=0)
-        fn = lambda: sdf(pts)
-        what = "oracle/port.py CachedSDFPort (op-for-op torch-cpu restatement of sdf.py:535-571)"
-        wl = "C2 CachedSDF(drill, res=0.005) value+gradient"
-    else:
-        tp_open3d.QUERY_METHOD = "bvh"
-        nl = (100, 51) if args.workload == "mesh10k" else (250, 101)
-        v, f = workloads.bumpy_sphere(*nl)
-        mesh = port.MeshPort(vertices=v, faces=f)
-        sample = 400_000
-        pts = workloads.uniform_points(sample, v.min(0) - 0.05, v.max(0) + 0.05, seed=2)
-        fn = lambda: mesh.closest_point(pts)
-        what = "oracle MeshPort.closest_point over the OpenMP BVH evaluator (sdf.py:122-172 restated)"
-        wl = f"MeshSDF on {len(f)}-triangle bumpy sphere"
+    arm = cpu_arm(args.workload)
+    probe = max(1000, arm.max_n // 20)
+    cores, tried = pick_cpu_threads(lambda: arm.run(probe))
+    # bounded sample: measure the host's throughput on a small slice, then size one step so that K + W of them fit
+    # the budget (never more than the arm's full sample)
+    t0 = time.perf_counter()
+    arm.run(probe)
+    per_point = (time.perf_counter() - t0) / probe
+    n = int(REFERENCE_ARM_BUDGET_S / (args.steps + max(args.warmup, 1)) / per_point)
+    n = max(1000, min(arm.max_n, n))
+    sample = n * arm.units_per_point
+    fn = lambda: arm.run(n)         # noqa: E731
+    wl = arm.label
+    what = (f"{n} points per step ({sample} units); {arm.what}; {cores} host threads = the fastest of "
+            f"{sorted(tried)} tried on {usable_cpus()} usable CPUs")
     for _ in range(max(args.warmup, 1)):
         fn()
     t0 = time.perf_counter()
@@ -479,9 +585,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl, "sample_points_per_step": sample},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} points per step; {what}; host threads {cores}"},
+            "config": {"workload": wl, "sample_units_per_step": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": what},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -564,18 +669,22 @@ def main():
 
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and hasattr(wl, "cpu_setup"):
-        from oracle import _geom
-        torch.set_num_threads(os.cpu_count() or 1)
-        sample = wl.cpu_setup()
-        wl.cpu_step()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if hasattr(wl, "cpu_setup"):        # same tables / points as the GPU arm
+            sample = wl.cpu_setup()
+            cpu_step = wl.cpu_step
+        else:
+            arm = cpu_arm(args.workload)
+            sample = f"{arm.max_n} points per step; {arm.what}"
+            cpu_step = lambda: (arm.run(arm.max_n), arm.max_n * arm.units_per_point)[1]      # noqa: E731
+        cpu_threads, tried = pick_cpu_threads(cpu_step)
+        sample += f"; {cpu_threads} host threads = the fastest of {sorted(tried)} tried"
         t0 = time.perf_counter()
         done = 0
         while time.perf_counter() - t0 < 8.0:
-            done += wl.cpu_step()
+            done += cpu_step()
         dt = time.perf_counter() - t0
-        cpu = {"value": done / dt, "unit": UNIT, "cores": max(torch.get_num_threads(), _geom.num_threads()),
-               "kind": "port", "sample": sample}
+        cpu = {"value": done / dt, "unit": UNIT, "cores": cpu_threads, "kind": "port", "sample": sample}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

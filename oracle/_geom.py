@@ -48,6 +48,8 @@ def lib():
         L.orc_count_intersections_bvh.argtypes = [ctypes.c_void_p, fp, i64, ip]
         L.orc_count_intersections_bvh.restype = None
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_set_num_threads.argtypes = [ctypes.c_int]
+        L.orc_set_num_threads.restype = None
         _lib = L
     return _lib
 
@@ -108,3 +110,8 @@ class TriangleSoup:
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n):
+    """OpenMP threads of the evaluators from now on."""
+    lib().orc_set_num_threads(int(n))

@@ -343,6 +343,16 @@ void orc_count_intersections_bvh(const void *h, const float *rays, int64_t N, in
     }
 }
 
+/* Threads used by the parallel loops from now on (no-op without OpenMP or for n < 1). */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP
