@@ -662,6 +662,23 @@ def _fp32_floor(x):
     return f if float(f) <= x else np.nextafter(f, np.float32(-np.inf))
 
 
+def fast_index_band(lo, hi, n):
+    """(inv_res32, idx_certain) of one grid axis for the kernels' fast voxel index.
+
+    The kernels estimate the index as q = (p - fp32(lo)) * inv_res32 in fp32 and accept rint(q) when
+    |q - rint(q)| <= idx_certain; closer to a cell boundary than that, they evaluate the reference's formula
+    round((p - lo) / res) exactly (fp64 or fp32, by the dtype torch infers for the range).  `err` bounds
+    |q - (p - lo) / res| in cells: rounding lo to fp32, the fp32 subtraction, the rounding of inv_res32 and the fp32
+    product, with a 4x safety factor; the identity "certain => same index" is checked on adversarial inputs by
+    tests/test_index_band.py.  idx_certain = -1 sends every point down the exact path."""
+    res = (hi - lo) / (n - 1) if n > 1 else float("inf")
+    if not (n > 1 and math.isfinite(res) and res > 0):
+        return 0.0, -1.0
+    scale = max(abs(lo), abs(hi)) + (hi - lo)
+    err = 4.0 * scale * 2.0 ** -24 / res + (n + 4) * 2.0 ** -22
+    return float(np.float32(1.0 / res)), max(0.5 - (4.0 * err + 1e-6), -1.0)
+
+
 class CachedSDF(ObjectFrameSDF):
     """SDF via nearest-voxel lookup of precomputed value and gradient tables."""
 
@@ -770,15 +787,7 @@ class CachedSDF(ObjectFrameSDF):
                 d.valid_lo[k], d.valid_hi[k] = float(_fp32_ceil(lo[k])), float(_fp32_floor(hi[k]))
             d.bb_min[k] = float(bb[k, 0])
             d.bb_max[k] = float(bb[k, 1])
-            # fast fp32 index estimate + the band around cell boundaries in which the exact formula is used
-            if shape[k] > 1 and math.isfinite(d.res64[k]) and d.res64[k] > 0:
-                d.inv_res32[k] = float(np.float32(1.0 / d.res64[k]))
-                scale = max(abs(lo[k]), abs(hi[k])) + (hi[k] - lo[k])
-                err = 4.0 * scale * 2.0 ** -24 / d.res64[k] + (shape[k] + 4) * 2.0 ** -22
-                d.idx_certain[k] = max(0.5 - (4.0 * err + 1e-6), -1.0)
-            else:
-                d.inv_res32[k] = 0.0
-                d.idx_certain[k] = -1.0          # always take the exact path
+            d.inv_res32[k], d.idx_certain[k] = fast_index_band(lo[k], hi[k], shape[k])
             if shape[k] > 1:
                 res_max = max(res_max, d.res64[k])
         gt_native = None
