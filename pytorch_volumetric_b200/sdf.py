@@ -679,6 +679,28 @@ def fast_index_band(lo, hi, n):
     return float(np.float32(1.0 / res)), max(0.5 - (4.0 * err + 1e-6), -1.0)
 
 
+def grid_prune_margin(values, lo, hi, bb):
+    """Margin m such that a BOUNDING_BOX CachedSDF never returns less than dist(q, bb) - m, for ANY query q.
+
+    The composed kernels skip a sub-SDF when dist(q, bb) - m already exceeds the running minimum, so the bound must
+    be exact, not typical.  Out of range the value IS dist(q, bb) (sdf.py:555-571).  In range it is the table entry
+    of the nearest voxel c, |q - c| <= half a cell diagonal, dist(., bb) is 1-Lipschitz, and t = max over the table
+    of (dist(c, bb) - value(c))+ is measured on the table itself, so the bound holds for any table contents:
+    value(c) >= dist(c, bb) - t >= dist(q, bb) - half_diag - t.  (1e-5 absorbs the kernels' fp32 arithmetic.)
+    values: (nx, ny, nz) table; lo / hi: per-axis range; bb: (3, 2) box the out-of-range rule measures against."""
+    shape = tuple(values.shape)
+    dev = values.device
+    bbt = torch.as_tensor(np.asarray(bb), dtype=torch.float64, device=dev)
+    per_axis = []
+    for k in range(3):
+        c = torch.linspace(lo[k], hi[k], shape[k], dtype=torch.float64, device=dev)
+        per_axis.append(torch.clamp(torch.maximum(bbt[k, 0] - c, c - bbt[k, 1]), min=0))
+    lb = torch.sqrt(per_axis[0][:, None, None] ** 2 + per_axis[1][None, :, None] ** 2 + per_axis[2][None, None, :] ** 2)
+    t = float(torch.clamp(lb - values.double(), min=0).max())
+    cell = [(hi[k] - lo[k]) / (shape[k] - 1) for k in range(3) if shape[k] > 1]
+    return 0.5 * math.sqrt(sum(r * r for r in cell)) + t + 1e-5
+
+
 class CachedSDF(ObjectFrameSDF):
     """SDF via nearest-voxel lookup of precomputed value and gradient tables."""
 
@@ -804,14 +826,7 @@ class CachedSDF(ObjectFrameSDF):
         # Pruning bound for the composed kernels: table value at the nearest voxel of q is never below
         # aabb_distance(q) - prune_margin.  t is measured on the table itself, so the bound holds for any table.
         if self.out_of_bounds_strategy == OutOfBoundsStrategy.BOUNDING_BOX:
-            coords = [torch.linspace(lo[k], hi[k], shape[k], dtype=torch.float64, device=self._cdev) for k in range(3)]
-            bbt = torch.tensor(bb, dtype=torch.float64, device=self._cdev)
-            per_axis = [torch.clamp(torch.maximum(bbt[k, 0] - coords[k], coords[k] - bbt[k, 1]), min=0) for k in range(3)]
-            lb = torch.sqrt(per_axis[0][:, None, None] ** 2 + per_axis[1][None, :, None] ** 2 +
-                            per_axis[2][None, None, :] ** 2)
-            t = float(torch.clamp(lb - self.voxels.raw_data.reshape(shape).double(), min=0).max())
-            half_diag = 0.5 * math.sqrt(sum(d.res64[k] ** 2 for k in range(3) if shape[k] > 1))
-            margin = half_diag + t + 1e-5
+            margin = grid_prune_margin(self.voxels.raw_data.reshape(shape), lo, hi, bb)
             if math.isfinite(margin):
                 d.prune_margin = margin
                 flags |= nat.PVB_GRID_PRUNE_OK
