@@ -104,3 +104,25 @@ def test_random_axes_have_no_counterexample():
             k_fast, certain = device_estimate(q, lo, hi, n)
             wrong = certain & (k_fast.astype(np.int64) != exact_index(q, lo, hi, n, fp32_mode))
             assert not wrong.any(), (lo, hi, n, fp32_mode, q[wrong][:3])
+
+
+def test_fp32_range_bounds_equal_the_fp64_comparison():
+    """The kernels test fp32 p against host-rounded fp32 bounds instead of converting p to fp64 and comparing with
+    the fp64 range (reference: torch compares the fp32 points with fp64 min / max by promotion): identical masks,
+    including the fp32 neighbours of both bounds."""
+    from pytorch_volumetric_b200.sdf import _fp32_ceil, _fp32_floor
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        lo = float(rng.uniform(-1, 1) * 10 ** rng.uniform(-4, 3))
+        hi = lo + float(10 ** rng.uniform(-4, 2))
+        vlo, vhi = np.float32(_fp32_ceil(lo)), np.float32(_fp32_floor(hi))
+        p = [np.float32(lo), np.float32(hi)]
+        for seed in list(p):
+            up, down = seed, seed
+            for _ in range(3):
+                up = np.nextafter(up, np.float32(np.inf)); down = np.nextafter(down, np.float32(-np.inf))
+                p += [up, down]
+        p = np.concatenate([np.array(p, dtype=np.float32), rng.uniform(lo - 1, hi + 1, 1000).astype(np.float32)])
+        want = (p.astype(np.float64) >= lo) & (p.astype(np.float64) <= hi)
+        got = (p >= vlo) & (p <= vhi)
+        assert np.array_equal(want, got), (lo, hi)
