@@ -153,3 +153,25 @@ def test_port_equals_live_reference_source(tmp_path, oracle_lib):
                                                                 "pytorch_kinematics", "arm_pytorch_utilities",
                                                                 "matplotlib")]:
             del sys.modules[m]
+
+
+def test_port_robot_equals_reference_golden(tmp_path, oracle_lib):
+    """RobotSDFPort on the procedural twin of the reference's tests/offset_wrench.urdf reproduces the vectors the
+    unmodified reference produced (oracle/make_golden.py: ref_robot_wrench) -- FK + offset composition bit-exact,
+    values / gradients bit-exact on the reference-built link table.  Runs without /root/reference."""
+    from oracle import tp_pytorch_kinematics as opk
+    from test_gpu_composed import write_wrench_urdf
+    z = golden("ref_robot_wrench")
+    urdf = write_wrench_urdf(str(tmp_path))
+    chain = opk.build_serial_chain_from_urdf(open(urdf).read(), "offset_wrench")
+    shape = tuple(int(s) for s in z["table_shape"])
+    tables = (torch.from_numpy(z["table_val"]).reshape(shape), torch.from_numpy(z["table_grad"]))
+    rp = port.RobotSDFPort(chain, path_prefix=str(tmp_path),
+                           link_sdf_factory=port.cache_link_sdf_factory_port(resolution=0.004, padding=0.05,
+                                                                             tables=tables))
+    np.testing.assert_allclose(np.array(rp.sdf.sdfs[0].ranges), z["ranges"], atol=1e-12)
+    rp.set_joint_configuration(torch.from_numpy(z["th"]))
+    assert np.array_equal(rp.object_to_link.get_matrix().numpy(), z["obj_to_link"])
+    v, g = rp(torch.from_numpy(z["q"]))
+    assert np.array_equal(v.numpy(), z["val"]) and np.array_equal(g.numpy(), z["grad"], equal_nan=True)
+    np.testing.assert_array_equal(rp.surface_bounding_box(padding=0.05).numpy(), z["bbox"])
