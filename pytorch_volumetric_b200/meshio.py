@@ -10,24 +10,28 @@ import numpy as np
 
 
 def read_obj(path):
+    """Positions (`v x y z [...]`) and faces (`f a[/t[/n]] ...`, 1-based or negative = relative to the vertices read
+    so far); polygons become triangle fans; every other record (vt, vn, g, o, s, usemtl, comments) is skipped."""
     verts = []
     faces = []
     with open(path, "r", errors="ignore") as fh:
         for line in fh:
-            if len(line) < 2:
+            t = line.split()
+            if not t:
                 continue
-            if line[0] == "v" and line[1] in " \t":
-                t = line.split()
+            if t[0] == "v":
                 verts.append((float(t[1]), float(t[2]), float(t[3])))
-            elif line[0] == "f" and line[1] in " \t":
+            elif t[0] == "f":
                 corner = []
-                for tok in line.split()[1:]:
+                for tok in t[1:]:
                     k = int(tok.partition("/")[0])
                     corner.append(k - 1 if k > 0 else len(verts) + k)
                 for j in range(2, len(corner)):
                     faces.append((corner[0], corner[j - 1], corner[j]))
     v = np.asarray(verts, dtype=np.float64).reshape(-1, 3)
     f = np.asarray(faces, dtype=np.int32).reshape(-1, 3)
+    if len(f) and (f.min() < 0 or f.max() >= len(v)):
+        raise RuntimeError(f"OBJ face refers to a vertex that does not exist: {path}")
     return v, f
 
 

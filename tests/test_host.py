@@ -64,15 +64,15 @@ def test_product_never_imports_oracle():
                 assert "liborc_geom" not in src, fn
 
 
-@pytest.mark.parametrize("name", ["probe", "wrench", "drill"])
-def test_bvh_builder_invariants(name, built_lib):
+def _check_bvh(v32, f):
+    """Structural invariants of pvb_bvh_build's output: every face once, BFS layout, boxes nest and contain their
+    triangles, every node reachable exactly once, traversal stack bound."""
     from pytorch_volumetric_b200 import _native
-    v, f = workloads.fixture_mesh(name)
-    v32 = v.astype(np.float32)
     nodes_raw, tris, depth = _native.bvh_build(v32, f)
     nodes = nodes_raw.view(np.float32).reshape(-1, 32)
     child = nodes_raw.view(np.int32).reshape(-1, 32)[:, 24:28]
     n_nodes = len(nodes)
+    assert n_nodes >= 1
     assert 3 * depth + 2 <= 64
     face_of = tris.view(np.int32)[:, 3]
     assert np.array_equal(np.sort(face_of), np.arange(len(f)))        # a permutation of the faces
@@ -110,6 +110,41 @@ def test_bvh_builder_invariants(name, built_lib):
                 tv = tris[first:first + cnt][:, [0, 1, 2, 4, 5, 6, 8, 9, 10]].reshape(-1, 3)
                 assert (tv >= lo).all() and (tv <= hi).all()
     assert (seen_tri == 1).all() and (seen_node == 1).all()
+    return n_nodes, depth
+
+
+@pytest.mark.parametrize("name", ["probe", "wrench", "drill"])
+def test_bvh_builder_invariants(name, built_lib):
+    v, f = workloads.fixture_mesh(name)
+    _check_bvh(v.astype(np.float32), f)
+
+
+def test_bvh_builder_degenerate_inputs(built_lib):
+    """Inputs that break naive SAH builders: a single triangle, many coincident triangles (zero-extent centroid
+    boxes: no split plane exists), zero-area triangles, a flat sheet (one axis has no extent), a strongly skewed
+    size distribution, and a large random soup (depth bound of the wide tree)."""
+    rng = np.random.default_rng(0)
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
+    one = np.array([[0, 1, 2]], dtype=np.int32)
+    assert _check_bvh(tri, one)[0] == 1
+    _check_bvh(tri, np.repeat(one, 1000, axis=0))                                   # 1000 identical triangles
+    pts = np.zeros((3, 3), dtype=np.float32)
+    _check_bvh(pts, np.repeat(one, 37, axis=0))                                     # all vertices at one point
+    line = np.array([[0, 0, 0], [1, 1, 1], [2, 2, 2], [3, 3, 3]], dtype=np.float32)
+    _check_bvh(line, np.array([[0, 1, 2], [1, 2, 3], [0, 2, 3]], dtype=np.int32))   # zero-area (collinear)
+    g = np.stack(np.meshgrid(np.arange(40), np.arange(40), indexing="ij"), -1).reshape(-1, 2)
+    sheet = np.concatenate([g, np.zeros((len(g), 1))], 1).astype(np.float32)        # flat in z
+    idx = np.arange(40 * 40).reshape(40, 40)
+    quads = np.stack([idx[:-1, :-1], idx[1:, :-1], idx[1:, 1:], idx[:-1, 1:]], -1).reshape(-1, 4)
+    _check_bvh(sheet, np.concatenate([quads[:, [0, 1, 2]], quads[:, [0, 2, 3]]]).astype(np.int32))
+    v = rng.normal(size=(3000, 3)).astype(np.float32)
+    v[:10] *= 1e4                                                                   # a few huge triangles over many tiny
+    _check_bvh(v, rng.integers(0, 3000, size=(5000, 3)).astype(np.int32))
+    v = rng.uniform(-1, 1, size=(60_000, 3)).astype(np.float32)
+    c = rng.integers(0, 60_000, size=120_000)
+    f = np.stack([c, (c + 1) % 60_000, (c + 2) % 60_000], 1).astype(np.int32)
+    n_nodes, depth = _check_bvh(v, f)
+    assert depth <= 20
 
 
 def test_grid_helpers_match_port():
@@ -240,3 +275,64 @@ def test_sharding_world_size_2_gloo(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port_no = s.getsockname()[1]; s.close()
     mp.spawn(_gloo_worker, args=(2, port_no, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
+
+
+def test_bvh_builder_rejects_bad_meshes(built_lib):
+    from pytorch_volumetric_b200 import _native
+    v = np.zeros((3, 3), np.float32)
+    for faces in (np.zeros((0, 3), np.int32), np.array([[0, 1, 5]], np.int32), np.array([[0, -1, 2]], np.int32)):
+        with pytest.raises(_native.NativeLibraryError):
+            _native.bvh_build(v, faces)
+
+
+def test_mesh_readers_edge_cases(tmp_path):
+    """OBJ: indentation, CRLF, comments, v/vt/vn corner syntax, negative (relative) indices, quads and n-gons as
+    fans, vertex colours; binary and ASCII STL; error behaviour."""
+    import struct
+    from pytorch_volumetric_b200 import meshio
+    obj = tmp_path / "m.obj"
+    obj.write_text("# comment\r\n"
+                   "mtllib x.mtl\r\n"
+                   "  v 0 0 0 1.0 0.5 0.25\r\n"
+                   "v 1 0 0\r\n"
+                   "\tv 1 1 0\r\n"
+                   "v 0 1 0\r\n"
+                   "vn 0 0 1\r\nvt 0.5 0.5\r\n"
+                   "v 0.5 0.5 1\r\n"
+                   "g part\r\ns off\r\n"
+                   "f 1/1/1 2/1/1 3/1/1 4/1/1\r\n"          # quad -> 2 triangles
+                   "f -5//1 -4//1 -1//1\r\n"                # relative indices
+                   "f 1 2 3 4 5\r\n")                       # pentagon -> 3 triangles
+    v, f = meshio.read_obj(str(obj))
+    assert v.shape == (5, 3) and v.dtype == np.float64
+    assert f.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 4], [0, 1, 2], [0, 2, 3], [0, 3, 4]]
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nv 1 0 0\nf 1 2 7\n")
+    with pytest.raises(RuntimeError):
+        meshio.read_obj(str(bad))
+    empty = tmp_path / "empty.obj"
+    empty.write_text("v 0 0 0\n")
+    with pytest.raises(RuntimeError):
+        meshio.read_triangle_mesh(str(empty))
+    with pytest.raises(RuntimeError):
+        meshio.read_triangle_mesh(str(tmp_path / "mesh.ply"))
+    # STL, both encodings, same triangles
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]], [[0, 0, 1], [1, 0, 1], [0, 1, 1]]], dtype=np.float32)
+    b = tmp_path / "b.stl"
+    with open(b, "wb") as fh:
+        fh.write(b"binary stl".ljust(80, b" ")); fh.write(struct.pack("<I", len(tri)))
+        for t in tri:
+            fh.write(struct.pack("<3f", 0, 0, 1)); fh.write(t.tobytes()); fh.write(b"\x00\x00")
+    a = tmp_path / "a.stl"
+    a.write_text("solid s\n" + "".join(
+        "facet normal 0 0 1\n outer loop\n" + "".join(f"  vertex {p[0]} {p[1]} {p[2]}\n" for p in t) +
+        " endloop\nendfacet\n" for t in tri) + "endsolid s\n")
+    for path in (a, b):
+        v, f = meshio.read_triangle_mesh(str(path))
+        assert np.array_equal(v[f], tri.astype(np.float64))
+    # write_obj round trip keeps every bit of the fp64 positions
+    vv = np.random.default_rng(0).normal(size=(7, 3))
+    ff = np.array([[0, 1, 2], [3, 4, 5], [6, 0, 3]], dtype=np.int32)
+    meshio.write_obj(str(tmp_path / "rt.obj"), vv, ff)
+    v2, f2 = meshio.read_obj(str(tmp_path / "rt.obj"))
+    assert np.array_equal(v2, vv) and np.array_equal(f2, ff)
