@@ -336,3 +336,51 @@ def test_mesh_readers_edge_cases(tmp_path):
     meshio.write_obj(str(tmp_path / "rt.obj"), vv, ff)
     v2, f2 = meshio.read_obj(str(tmp_path / "rt.obj"))
     assert np.array_equal(v2, vv) and np.array_equal(f2, ff)
+
+
+MIXED_URDF = """<robot name="mixed">
+  <link name="base"><visual><origin xyz="0 0 0.1" rpy="0.1 -0.2 0.3"/><geometry><mesh filename="a.obj" scale="2 2 2"/></geometry></visual>
+                    <visual><geometry><box size="0.1 0.1 0.1"/></geometry></visual></link>
+  <link name="l1"/>
+  <link name="l2"><visual><origin xyz="0.01 0 0" rpy="0 0 1.5"/><geometry><mesh filename="package://b.obj"/></geometry></visual></link>
+  <link name="l3"><visual><geometry><mesh filename="c.obj"/></geometry></visual></link>
+  <link name="tool"><visual><geometry><mesh filename="d.obj"/></geometry></visual></link>
+  <link name="side"><visual><geometry><mesh filename="e.obj"/></geometry></visual></link>
+  <joint name="j_fixed" type="fixed"><parent link="base"/><child link="l1"/><origin xyz="0 0 0.3" rpy="0 0.5 0"/></joint>
+  <joint name="j_rev" type="revolute"><parent link="l1"/><child link="l2"/><origin xyz="0.1 0.2 0" rpy="0.3 0 -0.4"/>
+         <axis xyz="1 1 0"/><limit lower="-3" upper="3"/></joint>
+  <joint name="j_pris" type="prismatic"><parent link="l2"/><child link="l3"/><origin xyz="0 0 0.2"/><axis xyz="0 -1 0.5"/></joint>
+  <joint name="j_cont" type="continuous"><parent link="l3"/><child link="tool"/><origin xyz="0.05 0 0" rpy="1.0 0 0"/><axis xyz="0 0 -1"/></joint>
+  <joint name="j_side" type="revolute"><parent link="l1"/><child link="side"/><axis xyz="0 0 1"/></joint>
+</robot>"""
+
+
+def test_urdf_chain_mixed_joint_types_match_oracle_restatement():
+    """Fixed / revolute / prismatic / continuous joints, rotated origins, non-axis-aligned and unnormalised axes,
+    links without visuals, non-mesh visuals, a side branch off the serial path: names, visuals and batched FK agree
+    with the oracle's restatement of pytorch_kinematics."""
+    import pytorch_volumetric_b200 as pv
+    from oracle import tp_pytorch_kinematics as opk
+    c1 = pv.build_serial_chain_from_urdf(MIXED_URDF, "tool")
+    c2 = opk.build_serial_chain_from_urdf(MIXED_URDF, "tool")
+    assert c1.get_joint_parameter_names() == c2.get_joint_parameter_names() == ["j_rev", "j_pris", "j_cont"]
+    names = c1.get_frame_names(exclude_fixed=False)
+    assert names == c2.get_frame_names(exclude_fixed=False)
+    assert not any("side" in n for n in names)
+    for n in names:
+        v1, v2 = c1.find_frame(n).link.visuals, c2.find_frame(n).link.visuals
+        assert [(v.geom_type, v.geom_param) for v in v1] == [(v.geom_type, v.geom_param) for v in v2], n
+        for a, b in zip(v1, v2):
+            assert torch.allclose(a.offset.get_matrix(), b.offset.get_matrix(), atol=1e-7)
+    g = torch.Generator().manual_seed(0)
+    th = torch.randn(9, 3, generator=g)
+    f1, f2 = c1.forward_kinematics(th, end_only=False), c2.forward_kinematics(th, end_only=False)
+    assert set(f1) == set(f2)
+    for k in f2:
+        assert f1[k].get_matrix().shape == (9, 4, 4)
+        assert torch.allclose(f1[k].get_matrix(), f2[k].get_matrix(), atol=2e-6), k
+    one1, one2 = c1.forward_kinematics(th[0], end_only=False), c2.forward_kinematics(th[0], end_only=False)
+    for k in one2:
+        assert torch.allclose(one1[k].get_matrix(), one2[k].get_matrix(), atol=2e-6), k
+    assert torch.allclose(c1.forward_kinematics(th, end_only=True).get_matrix(),
+                          c2.forward_kinematics(th, end_only=True).get_matrix(), atol=2e-6)
