@@ -18,7 +18,6 @@ chamfer.py:14, tests/test_model_to_sdf.py:278):
                                   revolute: Rodrigues rotation about the axis
                                   prismatic: translation along the axis
 """
-import math
 import types
 import xml.etree.ElementTree as ET
 
