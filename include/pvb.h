@@ -150,7 +150,8 @@ int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_t n, uint32
                    float *out_normal, void *workspace, int64_t workspace_bytes, void *stream);
 /* Optional DEVICE scratch for the tree-walk kernels (pvb_mesh_query, pvb_chamfer): with at least
  * pvb_query_workspace(n) bytes, large batches are spatially binned (counting sort into Morton cells) and walked
- * in that order, which keeps warps coherent; results land in the original slots.  0 / NULL = walk in input order. */
+ * in that order, which keeps warps coherent; results land in the original slots.  0 / NULL (or a pointer that is
+ * not 16-byte aligned) = walk in input order. */
 int64_t pvb_query_workspace(int64_t n);
 
 /* ---- CachedSDF.__call__ (sdf.py:535-571) and outside_surface (sdf.py:593-602) ----

@@ -1125,7 +1125,9 @@ static const uint32_t *sort_queries(const pvb_sdf_desc *obj, const float *pts, l
                                     void *workspace, size_t workspace_bytes, cudaStream_t stream, int *rc) {
     *rc = PVB_OK;
     static const int enabled = [] { const char *e = getenv("PVB_SORT_QUERIES"); return e ? atoi(e) : 1; }();
-    if (!enabled || !workspace || n < kSortMinPoints || n >= (1ll << 32) || workspace_bytes < sort_workspace_bytes(n))
+    // (the scan moves the counters as uint4: an unaligned scratch pointer simply means no binning)
+    if (!enabled || !workspace || ((uintptr_t)workspace & 15) || n < kSortMinPoints || n >= (1ll << 32) ||
+        workspace_bytes < sort_workspace_bytes(n))
         return nullptr;
     uint32_t *hist = reinterpret_cast<uint32_t *>(workspace);
     uint32_t *cell = hist + kSortCells;
