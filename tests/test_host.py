@@ -384,3 +384,39 @@ def test_urdf_chain_mixed_joint_types_match_oracle_restatement():
         assert torch.allclose(one1[k].get_matrix(), one2[k].get_matrix(), atol=2e-6), k
     assert torch.allclose(c1.forward_kinematics(th, end_only=True).get_matrix(),
                           c2.forward_kinematics(th, end_only=True).get_matrix(), atol=2e-6)
+
+
+def test_grid_descriptor_from_reference_table_without_gpu():
+    """CachedSDF._make_desc (the host half of pvb_grid_lookup's contract) on the reference-built golden table, with
+    CPU tensors standing in for device memory: lattice, dtype mode, in-range bounds, index band, pruning margin."""
+    from helpers import golden
+    from pytorch_volumetric_b200 import sdf as S, _native as nat
+    from pytorch_volumetric_b200.voxel import GridView
+    z = golden("ref_cachedsdf_probe")
+    shape = tuple(int(s) for s in z["table_shape"])
+    for ranges, fp32_mode in (([tuple(r) for r in z["ranges"]], False),
+                              ([tuple(float(x) for x in r) for r in z["ranges"]], True)):
+        c = object.__new__(S.CachedSDF)
+        c.ranges = ranges
+        val = torch.from_numpy(z["table_val"]).reshape(shape)
+        c.voxels = GridView(val, ranges, invalid_value=None)
+        c.voxels_grad = torch.from_numpy(z["table_grad"])
+        c._table = torch.cat([val.reshape(-1, 1), c.voxels_grad], 1).contiguous()
+        c.bb = torch.from_numpy(z["bb"])
+        c._cdev = torch.device("cpu")
+        c.out_of_bounds_strategy = S.OutOfBoundsStrategy.BOUNDING_BOX
+        c.interpolation = "nearest"
+        d = c._make_desc()
+        assert d.kind == nat.PVB_KIND_GRID and list(d.dims) == list(shape) and d.table == c._table.data_ptr()
+        assert bool(d.flags & nat.PVB_GRID_INDEX_FP32) == fp32_mode      # numpy scalars -> fp64 index arithmetic
+        assert d.flags & nat.PVB_GRID_PRUNE_OK and not d.flags & nat.PVB_GRID_OOB_GT
+        for k in range(3):
+            lo, hi = float(ranges[k][0]), float(ranges[k][1])
+            assert d.min64[k] == lo and abs(d.res64[k] - (hi - lo) / (shape[k] - 1)) < 1e-15
+            assert d.valid_lo[k] >= lo - 1e-7 and d.valid_hi[k] <= hi + 1e-7
+            if not fp32_mode:       # fp32 bounds equivalent to the fp64 comparison: never outside the fp64 range
+                assert float(d.valid_lo[k]) >= lo and float(d.valid_hi[k]) <= hi
+            assert (d.inv_res32[k], d.idx_certain[k]) == tuple(np.float32(x) for x in S.fast_index_band(lo, hi, shape[k]))
+            assert d.bb_min[k] == np.float32(z["bb"][k, 0]) and d.bb_max[k] == np.float32(z["bb"][k, 1])
+        want = S.grid_prune_margin(val, [r[0] for r in ranges], [r[1] for r in ranges], z["bb"].astype(np.float32))
+        assert abs(d.prune_margin - want) < 1e-7
