@@ -1,0 +1,74 @@
+// Host build of the device building blocks (pvb_device.cuh) behind a small C interface for tests/test_hostsim.py.
+// Every loop body below is the per-thread work of the corresponding kernel: one call of grid_eval / mesh_eval /
+// sphere_eval / bvh_winding per query, with host pointers in the descriptor.  Test infrastructure only.
+#include "cuda_runtime.h"
+#include "../../pytorch_volumetric_b200/csrc/pvb_device.cuh"
+
+using namespace pvb;
+
+static inline f3 point(const float *pts, long long i) { return mk3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]); }
+
+extern "C" void sim_grid_lookup(const pvb_sdf_desc *g, const float *pts, long long n, float *val, float *grad,
+                                long long *key) {
+    NodeStage st; st.smem = nullptr; st.n = 0;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < n; ++i) {
+        long long k = -1;
+        // <kMesh = true>: the instantiation that can fall back to the mesh for PVB_GRID_OOB_GT, like grid_lookup_*<true>
+        const SdfOut o = grid_eval<true, false>(*g, st, point(pts, i), PVB_MESH_DEFAULT, (uint64_t)i, &k);
+        val[i] = o.val; grad[3 * i] = o.grad.x; grad[3 * i + 1] = o.grad.y; grad[3 * i + 2] = o.grad.z;
+        if (key) key[i] = k;
+    }
+}
+
+// the branchy variant the composed kernels use (<kBranchOOB = true>) must agree with the select-based one
+extern "C" void sim_grid_lookup_branchy(const pvb_sdf_desc *g, const float *pts, long long n, float *val, float *grad) {
+    NodeStage st; st.smem = nullptr; st.n = 0;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < n; ++i) {
+        const SdfOut o = grid_eval<false, true>(*g, st, point(pts, i), 0u, (uint64_t)i, nullptr);
+        val[i] = o.val; grad[3 * i] = o.grad.x; grad[3 * i + 1] = o.grad.y; grad[3 * i + 2] = o.grad.z;
+    }
+}
+
+extern "C" void sim_mesh_query(const pvb_sdf_desc *m, const float *pts, long long n, uint32_t mode, float *dist,
+                               float *grad, float *closest, int *face) {
+    NodeStage st; st.smem = nullptr; st.n = 0;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long i = 0; i < n; ++i) {
+        f3 c; int f = -1;
+        const SdfOut o = mesh_eval(*m, st, point(pts, i), mode, (uint64_t)i, &c, &f);
+        dist[i] = o.val; grad[3 * i] = o.grad.x; grad[3 * i + 1] = o.grad.y; grad[3 * i + 2] = o.grad.z;
+        if (closest) { closest[3 * i] = c.x; closest[3 * i + 1] = c.y; closest[3 * i + 2] = c.z; }
+        if (face) face[i] = f;
+    }
+}
+
+// crossing parity alone: the exact axis-aligned walk (closed meshes) and the watertight diagonal ray
+extern "C" void sim_parity(const pvb_sdf_desc *m, const float *pts, long long n, const float *dirs, int *parity_x,
+                           int *parity_ray) {
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    const float4 *nodes = reinterpret_cast<const float4 *>(m->nodes), *tris = reinterpret_cast<const float4 *>(m->tris);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long i = 0; i < n; ++i) {
+        if (parity_x) parity_x[i] = bvh_parity_x(nodes, st, tris, point(pts, i));
+        if (parity_ray) parity_ray[i] = bvh_parity(nodes, st, tris, point(pts, i), point(dirs, i));
+    }
+}
+
+extern "C" void sim_winding(const pvb_sdf_desc *m, const float *pts, long long n, float *w) {
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    const float4 *nodes = reinterpret_cast<const float4 *>(m->nodes), *tris = reinterpret_cast<const float4 *>(m->tris);
+    const float4 *wn = reinterpret_cast<const float4 *>(m->wn_nodes);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long i = 0; i < n; ++i) w[i] = bvh_winding(nodes, wn, st, tris, point(pts, i));
+}
+
+extern "C" void sim_sphere(float radius, const float *pts, long long n, float *val, float *grad) {
+    for (long long i = 0; i < n; ++i) {
+        const SdfOut o = sphere_eval(radius, point(pts, i));
+        val[i] = o.val; grad[3 * i] = o.grad.x; grad[3 * i + 1] = o.grad.y; grad[3 * i + 2] = o.grad.z;
+    }
+}
+
+extern "C" float sim_hash_normal(uint32_t seed, unsigned long long idx, uint32_t comp) { return hash_normal(seed, idx, comp); }

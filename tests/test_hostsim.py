@@ -1,0 +1,176 @@
+"""CPU tier: the DEVICE code of the kernels (pvb_device.cuh, compiled for the host by tests/hostsim) against the
+reference's golden vectors and the oracle -- the same assertions as the -m gpu parity tests, on the per-thread
+arithmetic of grid_eval / mesh_eval / the crossing-parity walks / sphere_eval.  What this cannot see is the kernel
+scaffolding around those functions (tiling, TMA staging, running min, stores); the -m gpu tests cover that."""
+import numpy as np
+import pytest
+import torch
+
+import hostsim_lib as hs
+import workloads
+from helpers import golden, port_mesh, pv_factory, ray_noise, classify_mesh_mismatch
+from pytorch_volumetric_b200 import _native as nat
+
+TOL = 1e-5
+
+
+def _golden_grid(z, val_key="table_val", grad_key="table_grad", ranges=None, **kw):
+    shape = tuple(int(s) for s in z["table_shape"])
+    ranges = [tuple(r) for r in z["ranges"]] if ranges is None else ranges
+    return hs.grid_desc(torch.from_numpy(z[val_key]).reshape(shape), torch.from_numpy(z[grad_key]), ranges, z["bb"], **kw)
+
+
+@pytest.mark.parametrize("name", ["probe", "drill"])
+def test_grid_eval_vs_reference_golden(name, built_lib):
+    z = golden(f"ref_cachedsdf_{name}")
+    d, keep = _golden_grid(z)
+    val, grad, key = hs.grid_lookup(d, z["q"])
+    inb = z["inbound"]
+    assert np.array_equal(key >= 0, inb)                        # in-range mask: bit-exact
+    assert np.array_equal(key[inb], z["keys"][inb])             # ravelled voxel key: bit-exact
+    assert np.array_equal(val[inb], z["val"][inb]) and np.array_equal(grad[inb], z["grad"][inb])     # pure gathers
+    oob = ~inb
+    assert np.abs(val[oob] - z["val"][oob]).max() <= 2 * np.spacing(np.abs(z["val"][oob]).max())
+    assert np.abs(grad[oob] - z["grad"][oob]).max() <= 3e-7
+    vb, gb = hs.grid_lookup(d, z["q"], branchy=True)             # the composed kernels' instantiation
+    assert np.array_equal(vb, val) and np.array_equal(gb, grad)
+
+
+def test_grid_eval_fp32_range_mode(built_lib):
+    z = golden("ref_cachedsdf_probe")
+    rng32 = [(float(a), float(b)) for a, b in z["ranges_f32range"]]
+    d, keep = _golden_grid(z, "table_val_f32range", "table_grad_f32range", ranges=rng32)
+    assert d.flags & nat.PVB_GRID_INDEX_FP32
+    val, grad, key = hs.grid_lookup(d, z["q"])
+    inb = z["inbound_f32range"]
+    assert np.array_equal(key >= 0, inb) and np.array_equal(key[inb], z["keys_f32range"][inb])
+    assert np.array_equal(val[inb], z["val_f32range"][inb]) and np.array_equal(grad[inb], z["grad_f32range"][inb])
+
+
+def test_grid_eval_boundary_points_take_the_exact_path(built_lib):
+    """Points a few ulps around every cell boundary of every axis: the key still equals the reference formula
+    (oracle port, fp64 index arithmetic), i.e. the rare out-of-line exact path is wired correctly."""
+    from oracle import port
+    z = golden("ref_cachedsdf_probe")
+    d, keep = _golden_grid(z)
+    shape = tuple(int(s) for s in z["table_shape"])
+    c = port.CachedSDFPort("probe", float(z["resolution"]), z["range_in"], port.MeshSDFPort(port_mesh("probe")),
+                           tables=(torch.from_numpy(z["table_val"]).reshape(shape), torch.from_numpy(z["table_grad"])))
+    rng = np.random.default_rng(0)
+    lo = np.array([r[0] for r in z["ranges"]]); hi = np.array([r[1] for r in z["ranges"]])
+    pts = []
+    for ax in range(3):
+        res = (hi[ax] - lo[ax]) / (shape[ax] - 1)
+        b = (lo[ax] + (np.arange(shape[ax] - 1) + 0.5) * res).astype(np.float32)
+        for step in range(-3, 4):
+            col = b.copy()
+            for _ in range(abs(step)):
+                col = np.nextafter(col, np.float32(np.inf if step > 0 else -np.inf))
+            p = rng.uniform(lo, hi, size=(len(col), 3)).astype(np.float32)
+            p[:, ax] = col
+            pts.append(p)
+    pts = np.concatenate(pts)
+    _, _, key = hs.grid_lookup(d, pts)
+    _, flat, inb = c.index_and_mask(torch.from_numpy(pts))
+    assert np.array_equal(key >= 0, inb.numpy())
+    assert np.array_equal(key[inb.numpy()], flat.numpy()[inb.numpy()])
+
+
+def test_grid_eval_gt_strategy(built_lib):
+    from pytorch_volumetric_b200.sdf import OutOfBoundsStrategy
+    z = golden("ref_cachedsdf_probe")
+    d, keep = _golden_grid(z, strategy=OutOfBoundsStrategy.LOOKUP_GT_SDF, gt_obj=pv_factory("probe"))
+    n = len(z["val_gt"])
+    val, grad, _ = hs.grid_lookup(d, z["q"][:n])
+    inb = z["inbound"][:n]
+    assert np.array_equal(val[inb], z["val_gt"][inb])
+    assert np.abs(val[~inb] - z["val_gt"][~inb]).max() < 1e-6
+    assert (np.abs(grad[~inb] - z["grad_gt"][~inb]).max(axis=-1) > 1e-5).mean() < 2e-3
+
+
+@pytest.mark.parametrize("name", ["probe", "wrench", "drill"])
+def test_mesh_eval_vs_reference_golden(name, built_lib):
+    z = golden(f"ref_meshsdf_{name}")
+    obj = pv_factory(name)
+    d, keep = hs.mesh_desc(obj)
+    dist, grad, closest, face = hs.mesh_query(d, z["pts"])
+    sign_bad = (np.sign(dist) != np.sign(z["distance"])) & (np.abs(z["distance"]) > 1e-6)
+    assert sign_bad.mean() <= (0.0 if obj.is_closed else 2e-3)
+    ok = ~sign_bad
+    bad_v, bad_g, rep = classify_mesh_mismatch(dist[ok], grad[ok], z["distance"][ok], z["gradient"][ok], TOL)
+    assert bad_v == 0 and bad_g == 0, rep
+    assert (face >= 0).all() and (face < len(workloads.fixture_mesh(name)[1])).all()
+
+
+@pytest.mark.parametrize("name,n", [("probe", 8000), ("wrench", 8000), ("scene_overlap", 4000), ("scene_separated", 4000)])
+def test_mesh_eval_vs_oracle(name, n, oracle_lib, built_lib):
+    obj = pv_factory(name, ray_seed=5)
+    mesh = port_mesh(name)
+    v, _ = workloads.fixture_mesh(name)
+    pts = workloads.uniform_points(n, v.min(0) - 0.02, v.max(0) + 0.02, 21)
+    d, keep = hs.mesh_desc(obj)
+    dist, grad, closest, face = hs.mesh_query(d, pts)
+    c_ref, d_ref, g_ref, _ = mesh.closest_point(pts, compute_normal=True, ray_noise=ray_noise(5, n))
+    d_ref, g_ref = d_ref.numpy(), g_ref.numpy()
+    scale = float(np.abs(v).max())
+    assert np.abs(np.abs(dist) - np.abs(d_ref)).max() < 5e-6 * max(1.0, scale / 0.1)
+    sign_bad = (np.sign(dist) != np.sign(d_ref)) & (np.abs(d_ref) > 1e-6)
+    assert sign_bad.mean() <= (0.0 if obj.is_closed else 2e-3)
+    ok = ~sign_bad
+    bad_v, bad_g, rep = classify_mesh_mismatch(dist[ok], grad[ok], d_ref[ok], g_ref[ok], TOL, coord_scale=scale)
+    assert bad_v == 0 and bad_g == 0, rep
+
+
+def test_jitter_hash_matches_the_host_mirror(built_lib):
+    """tests/helpers.py ray_noise (numpy) == pvb_device.cuh hash_normal, bit for bit."""
+    want = ray_noise(5, 1000)
+    got = np.array([[hs.lib().sim_hash_normal(5, i, c) for c in range(3)] for i in range(1000)], dtype=np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_axis_parity_is_exact_on_lattice_aligned_queries(oracle_lib, built_lib):
+    """Closed meshes: the +x walk with symbolic perturbation must give the true inside/outside even when the ray
+    passes exactly through vertices and along edges -- queries ON the vertex lattice of a box mesh and of the
+    bumpy sphere (y, z copied from mesh vertices), checked against an analytic / generic-direction answer."""
+    # axis-aligned box [0,1]^3, 12 triangles: rays through corners, along edges and through the face diagonals
+    v = np.array([[x, y, z] for x in (0., 1.) for y in (0., 1.) for z in (0., 1.)], dtype=np.float64)
+    f = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6],
+                  [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]], dtype=np.int32)
+    import pytorch_volumetric_b200 as pv
+    box = pv.MeshObjectFactory("box", mesh=(v, f))
+    assert box.is_closed
+    d, keep = hs.mesh_desc(box)
+    g = np.array([-0.5, 0.0, 0.25, 0.5, 0.75, 1.0, 1.5])
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    px, _ = hs.parity(d, pts)
+    strictly_inside = ((pts > 0) & (pts < 1)).all(1)
+    strictly_outside = ((pts < 0) | (pts > 1)).any(1)
+    assert (px[strictly_inside] == 1).all() and (px[strictly_outside] == 0).all()
+    # bumpy sphere: (y, z) of every query copied from a vertex, x swept: compare with a generic diagonal ray
+    vs, fs = workloads.bumpy_sphere(40, 21)
+    sph = pv.MeshObjectFactory("bumpy", mesh=(vs, fs))
+    d2, keep2 = hs.mesh_desc(sph)
+    rng = np.random.default_rng(0)
+    pick = rng.integers(0, len(vs), 3000)
+    q = vs[pick].astype(np.float32)
+    q[:, 0] = rng.uniform(vs[:, 0].min() - 0.02, vs[:, 0].max() + 0.02, len(q)).astype(np.float32)
+    dirs = np.tile(np.array([[0.5377, 0.6123, 0.5796]], dtype=np.float32), (len(q), 1))
+    px, pr = hs.parity(d2, q, dirs)
+    dist, _, _, _ = hs.mesh_query(d2, q, mode=0)
+    clear = np.abs(dist) > 1e-6                  # not on the surface itself
+    assert np.array_equal(px[clear], pr[clear])
+
+
+def test_winding_and_sphere(oracle_lib, built_lib):
+    from oracle import port
+    obj = pv_factory("probe")
+    d, keep = hs.mesh_desc(obj, with_winding=True)
+    v, f = workloads.fixture_mesh("probe")
+    pts = workloads.uniform_points(3000, v.min(0) - 0.02, v.max(0) + 0.02, 4)
+    w = hs.winding(d, pts)
+    w_ref = port.winding_number_port(v, f, pts.numpy())
+    assert np.abs(w - w_ref).max() < 0.05 and np.array_equal(np.abs(w) > 0.5, np.abs(w_ref) > 0.5)
+    p = workloads.uniform_points(1000, [-1] * 3, [1] * 3, 9)
+    val, grad = hs.sphere(0.3, p)
+    r = p.norm(dim=-1)
+    assert np.allclose(val, (r - 0.3).numpy(), atol=1e-6) and np.allclose(grad, (p / r[:, None]).numpy(), atol=1e-5)
