@@ -12,6 +12,12 @@
 namespace pvb {
 
 constexpr int kStack = 64;            // traversal stack entries per thread; the builder bounds the depth at 20
+
+// Traversal statistics hook: expands to nothing in the CUDA build; the host build of this header (tests/hostsim)
+// defines it to count node visits and triangle tests per query (reported in profiles/README.md).
+#ifndef PVB_STAT
+#define PVB_STAT(counter)
+#endif
 #define PVB_INF (__builtin_huge_valf())
 
 struct f3 { float x, y, z; };
@@ -102,6 +108,7 @@ __device__ __forceinline__ Closest bvh_closest(const float4 *__restrict__ gnodes
         --sp;
         const int ni = stack_n[sp];
         if (stack_d[sp] * kSlack > best.d2) continue;
+        PVB_STAT(closest_nodes)
         const float4 *n = node_ptr(gnodes, st, ni);
         const float4 lox = n[0], loy = n[1], loz = n[2], hix = n[3], hiy = n[4], hiz = n[5];
         const int4 ch = *reinterpret_cast<const int4 *>(n + 6);
@@ -127,6 +134,7 @@ __device__ __forceinline__ Closest bvh_closest(const float4 *__restrict__ gnodes
                 const unsigned code = (unsigned)~c[k];
                 const int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
                 for (int t = first; t < first + cnt; ++t) {
+                    PVB_STAT(closest_tris)
                     const float4 v0 = __ldg(tris + 3 * (size_t)t);
                     const float4 v1 = __ldg(tris + 3 * (size_t)t + 1);
                     const float4 v2 = __ldg(tris + 3 * (size_t)t + 2);
@@ -178,6 +186,7 @@ __device__ __forceinline__ int bvh_parity(const float4 *__restrict__ gnodes, con
     stack_n[sp++] = 0;
     while (sp > 0) {
         const int ni = stack_n[--sp];
+        PVB_STAT(parity_nodes)
         const float4 *n = node_ptr(gnodes, st, ni);
         const float4 lox = n[0], loy = n[1], loz = n[2], hix = n[3], hiy = n[4], hiz = n[5];
         const int4 ch = *reinterpret_cast<const int4 *>(n + 6);
@@ -205,6 +214,7 @@ __device__ __forceinline__ int bvh_parity(const float4 *__restrict__ gnodes, con
             const unsigned code = (unsigned)~c[k];
             const int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
             for (int t = first; t < first + cnt; ++t) {
+                PVB_STAT(parity_tris)
                 const float4 v0 = __ldg(tris + 3 * (size_t)t);
                 const float4 v1 = __ldg(tris + 3 * (size_t)t + 1);
                 const float4 v2 = __ldg(tris + 3 * (size_t)t + 2);
@@ -271,6 +281,7 @@ __device__ __forceinline__ int bvh_parity_x(const float4 *__restrict__ gnodes, c
     stack_n[sp++] = 0;
     while (sp > 0) {
         const int ni = stack_n[--sp];
+        PVB_STAT(parity_nodes)
         const float4 *n = node_ptr(gnodes, st, ni);
         const float4 loy = n[1], loz = n[2], hix = n[3], hiy = n[4], hiz = n[5];
         const int4 ch = *reinterpret_cast<const int4 *>(n + 6);
@@ -291,6 +302,7 @@ __device__ __forceinline__ int bvh_parity_x(const float4 *__restrict__ gnodes, c
             const unsigned code = (unsigned)~c[k];
             const int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
             for (int t = first; t < first + cnt; ++t) {
+                PVB_STAT(parity_tris)
                 const float4 v0 = __ldg(tris + 3 * (size_t)t);
                 const float4 v1 = __ldg(tris + 3 * (size_t)t + 1);
                 const float4 v2 = __ldg(tris + 3 * (size_t)t + 2);

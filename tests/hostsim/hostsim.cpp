@@ -2,6 +2,11 @@
 // Every loop body below is the per-thread work of the corresponding kernel: one call of grid_eval / mesh_eval /
 // sphere_eval / bvh_winding per query, with host pointers in the descriptor.  Test infrastructure only.
 #include "cuda_runtime.h"
+
+// traversal statistics: per-thread counters behind the header's PVB_STAT hook
+struct SimStats { long long closest_nodes, closest_tris, parity_nodes, parity_tris; };
+static thread_local SimStats t_stats = {0, 0, 0, 0};
+#define PVB_STAT(counter) ++t_stats.counter;
 #include "../../pytorch_volumetric_b200/csrc/pvb_device.cuh"
 
 using namespace pvb;
@@ -31,17 +36,25 @@ extern "C" void sim_grid_lookup_branchy(const pvb_sdf_desc *g, const float *pts,
     }
 }
 
+// stats_out (optional): totals over the n queries {closest nodes, closest triangles, parity nodes, parity triangles}
 extern "C" void sim_mesh_query(const pvb_sdf_desc *m, const float *pts, long long n, uint32_t mode, float *dist,
-                               float *grad, float *closest, int *face) {
+                               float *grad, float *closest, int *face, long long *stats_out) {
     NodeStage st; st.smem = nullptr; st.n = 0;
-#pragma omp parallel for schedule(dynamic, 256)
-    for (long long i = 0; i < n; ++i) {
-        f3 c; int f = -1;
-        const SdfOut o = mesh_eval(*m, st, point(pts, i), mode, (uint64_t)i, &c, &f);
-        dist[i] = o.val; grad[3 * i] = o.grad.x; grad[3 * i + 1] = o.grad.y; grad[3 * i + 2] = o.grad.z;
-        if (closest) { closest[3 * i] = c.x; closest[3 * i + 1] = c.y; closest[3 * i + 2] = c.z; }
-        if (face) face[i] = f;
+    long long a = 0, b = 0, c2 = 0, d2 = 0;
+#pragma omp parallel reduction(+ : a, b, c2, d2)
+    {
+        t_stats = SimStats{0, 0, 0, 0};
+#pragma omp for schedule(dynamic, 256)
+        for (long long i = 0; i < n; ++i) {
+            f3 c; int f = -1;
+            const SdfOut o = mesh_eval(*m, st, point(pts, i), mode, (uint64_t)i, &c, &f);
+            dist[i] = o.val; grad[3 * i] = o.grad.x; grad[3 * i + 1] = o.grad.y; grad[3 * i + 2] = o.grad.z;
+            if (closest) { closest[3 * i] = c.x; closest[3 * i + 1] = c.y; closest[3 * i + 2] = c.z; }
+            if (face) face[i] = f;
+        }
+        a += t_stats.closest_nodes; b += t_stats.closest_tris; c2 += t_stats.parity_nodes; d2 += t_stats.parity_tris;
     }
+    if (stats_out) { stats_out[0] = a; stats_out[1] = b; stats_out[2] = c2; stats_out[3] = d2; }
 }
 
 // crossing parity alone: the exact axis-aligned walk (closed meshes) and the watertight diagonal ray

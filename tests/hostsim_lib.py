@@ -52,12 +52,17 @@ def grid_lookup(desc, points, branchy=False):
     return val, grad, key
 
 
-def mesh_query(desc, points, mode=nat.PVB_MESH_DEFAULT):
+def mesh_query(desc, points, mode=nat.PVB_MESH_DEFAULT, stats=False):
+    """(dist, grad, closest, face) and, with stats=True, a dict of traversal counts per query."""
     p = _pts(points); n = len(p)
     dist, grad = np.empty(n, np.float32), np.empty((n, 3), np.float32)
     closest, face = np.empty((n, 3), np.float32), np.empty(n, np.int32)
+    st = np.zeros(4, np.int64)
     lib().sim_mesh_query(ctypes.byref(desc), _p(p), ctypes.c_longlong(n), ctypes.c_uint32(mode), _p(dist), _p(grad),
-                         _p(closest), _p(face))
+                         _p(closest), _p(face), _p(st))
+    if stats:
+        names = ("closest_nodes", "closest_tris", "parity_nodes", "parity_tris")
+        return dist, grad, closest, face, {k: float(v) / max(n, 1) for k, v in zip(names, st)}
     return dist, grad, closest, face
 
 
