@@ -174,3 +174,30 @@ def test_winding_and_sphere(oracle_lib, built_lib):
     val, grad = hs.sphere(0.3, p)
     r = p.norm(dim=-1)
     assert np.allclose(val, (r - 0.3).numpy(), atol=1e-6) and np.allclose(grad, (p / r[:, None]).numpy(), atol=1e-5)
+
+
+def test_c1_full_size_drill_grid_vs_oracle(oracle_lib, built_lib):
+    """BASELINE configs[0] (C1): 50^3 = 125 000 grid points over the drill's bounding box (padding 0.01)
+    + 1e-6 jitter, seed 0 -- the reference's own CPU-runnable case -- device code against the oracle's BVH
+    evaluator at full size."""
+    from oracle import tp_open3d
+    obj = pv_factory("drill", ray_seed=0)
+    mesh = port_mesh("drill")
+    bb = obj.bounding_box(padding=0.01)
+    axes = [torch.linspace(float(bb[k, 0]), float(bb[k, 1]), 50, dtype=torch.float64) for k in range(3)]
+    g = torch.Generator().manual_seed(0)
+    pts = (torch.cartesian_prod(*axes) + 1e-6 * torch.randn(125000, 3, generator=g, dtype=torch.float64)).float()
+    d, keep = hs.mesh_desc(obj)
+    dist, grad, closest, face = hs.mesh_query(d, pts)
+    prev = tp_open3d.QUERY_METHOD
+    tp_open3d.QUERY_METHOD = "bvh"
+    try:
+        _, d_ref, g_ref, _ = mesh.closest_point(pts, compute_normal=True, ray_noise=ray_noise(0, len(pts)))
+    finally:
+        tp_open3d.QUERY_METHOD = prev
+    d_ref, g_ref = d_ref.numpy(), g_ref.numpy()
+    assert np.abs(np.abs(dist) - np.abs(d_ref)).max() < 1e-5
+    sign_bad = (np.sign(dist) != np.sign(d_ref)) & (np.abs(d_ref) > 1e-6)
+    assert sign_bad.sum() == 0
+    bad_v, bad_g, rep = classify_mesh_mismatch(dist, grad, d_ref, g_ref, TOL, coord_scale=float(np.abs(bb).max()))
+    assert bad_v == 0 and bad_g == 0, rep
