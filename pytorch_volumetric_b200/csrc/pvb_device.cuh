@@ -544,4 +544,73 @@ __device__ __forceinline__ SdfOut sphere_eval(float radius, f3 p) {   // sdf.py:
     return o;
 }
 
+
+// ----------------------------------------------------------------------------
+// Composition primitives shared by the point-major and the configuration-major kernels (ComposedSDF.__call__,
+// sdf.py:392-433): the rigid transform into a sub-frame, the exact rejection bound, one "consider this sub-SDF"
+// step of the running argmin, and the gradient rotation back to the object frame.
+
+// Transform3d.transform_points: R p + t (sdf.py:399); rows r0..r2 of the 4x4 object->sub-frame matrix
+__device__ __forceinline__ f3 composed_xform(const float4 &r0, const float4 &r1, const float4 &r2, f3 v) {
+    return mk3(fmaf(r0.x, v.x, fmaf(r0.y, v.y, fmaf(r0.z, v.z, r0.w))),
+               fmaf(r1.x, v.x, fmaf(r1.y, v.y, fmaf(r1.z, v.z, r1.w))),
+               fmaf(r2.x, v.x, fmaf(r2.y, v.y, fmaf(r2.z, v.z, r2.w))));
+}
+
+// squared distance from q to the sub-SDF's box (0 inside)
+__device__ __forceinline__ float composed_aabb_lb2(const pvb_sdf_desc &d, f3 q) {
+    const float ex = fmaxf(fmaxf(d.bb_min[0] - q.x, q.x - d.bb_max[0]), 0.f);
+    const float ey = fmaxf(fmaxf(d.bb_min[1] - q.y, q.y - d.bb_max[1]), 0.f);
+    const float ez = fmaxf(fmaxf(d.bb_min[2] - q.z, q.z - d.bb_max[2]), 0.f);
+    return ex * ex + ey * ey + ez * ez;
+}
+
+// link_frame_to_obj_frame[i].transform_normals(g) = g @ inv(inv(M)[:3,:3]) = g @ M[:3,:3]
+// (sdf.py:380-383, 409): the double inversion cancels, no inverse is needed.
+__device__ __forceinline__ f3 composed_rotate_back(const float4 &r0, const float4 &r1, const float4 &r2, f3 g) {
+    return mk3(fmaf(g.x, r0.x, fmaf(g.y, r1.x, g.z * r2.x)), fmaf(g.x, r0.y, fmaf(g.y, r1.y, g.z * r2.y)),
+               fmaf(g.x, r0.z, fmaf(g.y, r1.z, g.z * r2.z)));
+}
+
+// Sub-SDF `s` (descriptor d, query q already in its frame) as a candidate for the running minimum
+// (best, bg, bs) of one point; bs < 0 = nothing evaluated yet.  Skipped without touching its table / tree when
+// provably not the argmin: value >= dist(q, box) - prune_margin (measured on the table for grids, fp32 slack for
+// closed meshes).  torch.argmin semantics (sdf.py:421): smallest value, first index on ties -- whatever the
+// visiting order.
+template <bool kMesh>
+__device__ __forceinline__ void composed_consider(const pvb_sdf_desc &d, const NodeStage &st, int s, f3 q,
+                                                  uint32_t mesh_mode, uint64_t idx, float &best, f3 &bg, int &bs) {
+    SdfOut o;
+    if (d.kind == PVB_KIND_GRID) {
+        if ((d.flags & PVB_GRID_PRUNE_OK) && bs >= 0) {
+            const float thr = best + d.prune_margin;
+            if (thr < 0.f || composed_aabb_lb2(d, q) > thr * thr) return;
+        }
+        o = grid_eval<kMesh, true>(d, st, q, mesh_mode, idx, nullptr);
+    } else if (kMesh && d.kind == PVB_KIND_MESH) {
+        // closed mesh, query outside its AABB: the value is +distance >= dist(q, AABB), so (a) skip it when that
+        // bound already exceeds the running min, (b) otherwise search only within the running min and (c) skip
+        // the parity walk -- all exact
+        float init_d2 = PVB_INF;
+        bool outside_box = false;
+        if ((d.flags & PVB_MESH_CLOSED) && (mesh_mode & PVB_MESH_SIGNED)) {
+            const float lb2 = composed_aabb_lb2(d, q);
+            outside_box = lb2 > 0.f;
+            if (outside_box && bs >= 0) {
+                const float thr = best + d.prune_margin;
+                if (thr < 0.f || lb2 > thr * thr) return;
+                if (best > 0.f) init_d2 = thr * thr;
+            }
+        }
+        int face;
+        o = mesh_eval(d, st, q, mesh_mode, idx, nullptr, &face, init_d2, outside_box);
+        if (face < 0) return;          // nothing within the running min: cannot be the argmin
+    } else {
+        o = sphere_eval(d.radius, q);
+    }
+    if (bs < 0 || o.val < best || (o.val == best && s < bs)) {
+        best = o.val; bg = o.grad; bs = s;
+    }
+}
+
 }  // namespace pvb

@@ -659,78 +659,28 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
                     r0 = __ldg(row); r1 = __ldg(row + 1); r2 = __ldg(row + 2);
                 }
             };
-            auto xform = [](const float4 &r0, const float4 &r1, const float4 &r2, f3 v) {
-                // Transform3d.transform_points: R p + t  (sdf.py:399)
-                return mk3(fmaf(r0.x, v.x, fmaf(r0.y, v.y, fmaf(r0.z, v.z, r0.w))),
-                           fmaf(r1.x, v.x, fmaf(r1.y, v.y, fmaf(r1.z, v.z, r1.w))),
-                           fmaf(r2.x, v.x, fmaf(r2.y, v.y, fmaf(r2.z, v.z, r2.w))));
-            };
-            auto aabb_lb2 = [](const pvb_sdf_desc &d, f3 q) {
-                const float ex = fmaxf(fmaxf(d.bb_min[0] - q.x, q.x - d.bb_max[0]), 0.f);
-                const float ey = fmaxf(fmaxf(d.bb_min[1] - q.y, q.y - d.bb_max[1]), 0.f);
-                const float ez = fmaxf(fmaxf(d.bb_min[2] - q.z, q.z - d.bb_max[2]), 0.f);
-                return ex * ex + ey * ey + ez * ez;
-            };
-            auto evaluate = [&](const pvb_sdf_desc &d, int s, int k, f3 q) {
-                SdfOut o;
-                const uint64_t idx = ((uint64_t)c * (uint64_t)n_pts + (uint64_t)(i0 + k)) * (uint64_t)n_sdf + (uint64_t)s;
-                if (d.kind == PVB_KIND_GRID) o = grid_eval<kMesh, true>(d, st, q, mesh_mode, idx, nullptr);
-                else if (kMesh && d.kind == PVB_KIND_MESH) {
-                    // closed mesh, query outside its AABB: the value is +distance >= dist(q, AABB), so (a) skip it
-                    // when that bound already exceeds the running min, (b) otherwise search only within the
-                    // running min and (c) skip the parity walk -- all exact
-                    float init_d2 = PVB_INF;
-                    bool outside_box = false;
-                    if ((d.flags & PVB_MESH_CLOSED) && (mesh_mode & PVB_MESH_SIGNED)) {
-                        const float lb2 = aabb_lb2(d, q);
-                        outside_box = lb2 > 0.f;
-                        if (outside_box && bs[k] >= 0) {
-                            const float thr = best[k] + d.prune_margin;
-                            if (thr < 0.f || lb2 > thr * thr) return;
-                            if (best[k] > 0.f) init_d2 = thr * thr;
-                        }
-                    }
-                    int face;
-                    o = mesh_eval(d, st, q, mesh_mode, idx, nullptr, &face, init_d2, outside_box);
-                    if (face < 0) return;          // nothing within the running min: cannot be the argmin
-                } else o = sphere_eval(d.radius, q);
-                // torch.argmin semantics (sdf.py:421): smallest value, first index on ties -- whatever the visiting order
-                if (bs[k] < 0 || o.val < best[k] || (o.val == best[k] && s < bs[k])) {
-                    best[k] = o.val; bg[k] = o.grad; bs[k] = s;
-                }
-            };
-
-            // (Evaluating the sub-SDF with the smallest AABB lower bound first -- an extra pass over all of them without
-            // table access -- saves lookups but measured 1.8x slower: the kernel is issue-bound; profiles/README.md.)
-            // every sub-SDF in visiting order, skipped when provably not the argmin
+            // every sub-SDF in visiting order, skipped when provably not the argmin (composed_consider,
+            // pvb_device.cuh).  (Evaluating the sub-SDF with the smallest AABB lower bound first -- an extra pass
+            // over all of them without table access -- saves lookups but measured 1.8x slower: the kernel is
+            // issue-bound; profiles/README.md.)
             for (int si = 0; si < n_sdf; ++si) {
                 const int s = descs.order[si];
                 const pvb_sdf_desc &d = descs.d[s];
                 float4 r0, r1, r2;
                 load_xf(s, r0, r1, r2);
-                const bool prunable = d.kind == PVB_KIND_GRID && (d.flags & PVB_GRID_PRUNE_OK);
 #pragma unroll
                 for (int k = 0; k < PTS; ++k) {
-                    const f3 q = xform(r0, r1, r2, p[k]);
-                    if (prunable && bs[k] >= 0) {
-                        // value >= dist(q, AABB) - margin: skip when that bound already exceeds the running min
-                        const float thr = best[k] + d.prune_margin;
-                        if (thr < 0.f || aabb_lb2(d, q) > thr * thr) continue;
-                    }
-                    evaluate(d, s, k, q);
+                    const uint64_t idx = ((uint64_t)c * (uint64_t)n_pts + (uint64_t)(i0 + k)) * (uint64_t)n_sdf + (uint64_t)s;
+                    composed_consider<kMesh>(d, st, s, composed_xform(r0, r1, r2, p[k]), mesh_mode, idx, best[k], bg[k],
+                                             bs[k]);
                 }
             }
-            // link_frame_to_obj_frame[i].transform_normals(g) = g @ inv(inv(M)[:3,:3]) = g @ M[:3,:3]
-            // (sdf.py:380-383, 409): the double inversion cancels, no inverse is needed.
             f3 go[PTS];
 #pragma unroll
             for (int k = 0; k < PTS; ++k) {
-                const int sb = max(bs[k], 0);
                 float4 r0, r1, r2;
-                load_xf(sb, r0, r1, r2);
-                go[k] = mk3(fmaf(bg[k].x, r0.x, fmaf(bg[k].y, r1.x, bg[k].z * r2.x)),
-                            fmaf(bg[k].x, r0.y, fmaf(bg[k].y, r1.y, bg[k].z * r2.y)),
-                            fmaf(bg[k].x, r0.z, fmaf(bg[k].y, r1.z, bg[k].z * r2.z)));
+                load_xf(max(bs[k], 0), r0, r1, r2);
+                go[k] = composed_rotate_back(r0, r1, r2, bg[k]);
             }
             const long long o_i = (long long)c * n_pts + i0;
             auto emit = [&](float *ov, float *og) {
@@ -852,32 +802,15 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
         int bs[kCmPts];
 #pragma unroll
         for (int k = 0; k < kCmPts; ++k) { best[k] = PVB_INF; bg[k] = mk3(0.f, 0.f, 0.f); bs[k] = -1; }
-        // One sub-SDF visit for the points of this thread that still need it: transform, AABB bound, lookup.
+        // One sub-SDF visit for the points of this thread that still need it: transform, AABB bound, lookup
+        // (same composed_xform / composed_consider as the point-major kernel: identical arithmetic, identical results)
         auto visit = [&](int s, const bool (&need)[kCmPts]) {
             const pvb_sdf_desc &d = descs.d[s];
             const float4 r0 = sm.xf[lane][3 * s], r1 = sm.xf[lane][3 * s + 1], r2 = sm.xf[lane][3 * s + 2];
-            const bool prunable = d.kind == PVB_KIND_GRID && (d.flags & PVB_GRID_PRUNE_OK);
 #pragma unroll
             for (int k = 0; k < kCmPts; ++k) {
                 if (!need[k]) continue;
-                // Transform3d.transform_points: R p + t  (sdf.py:399) -- same FMA order as the point-major kernel
-                const f3 q = mk3(fmaf(r0.x, p[k].x, fmaf(r0.y, p[k].y, fmaf(r0.z, p[k].z, r0.w))),
-                                 fmaf(r1.x, p[k].x, fmaf(r1.y, p[k].y, fmaf(r1.z, p[k].z, r1.w))),
-                                 fmaf(r2.x, p[k].x, fmaf(r2.y, p[k].y, fmaf(r2.z, p[k].z, r2.w))));
-                if (prunable && bs[k] >= 0) {     // stage 2: distance to the link AABB in the link frame
-                    const float thr = best[k] + d.prune_margin;
-                    const float ex = fmaxf(fmaxf(d.bb_min[0] - q.x, q.x - d.bb_max[0]), 0.f);
-                    const float ey = fmaxf(fmaxf(d.bb_min[1] - q.y, q.y - d.bb_max[1]), 0.f);
-                    const float ez = fmaxf(fmaxf(d.bb_min[2] - q.z, q.z - d.bb_max[2]), 0.f);
-                    if (thr < 0.f || ex * ex + ey * ey + ez * ez > thr * thr) continue;
-                }
-                SdfOut o;
-                if (d.kind == PVB_KIND_GRID) o = grid_eval<false, true>(d, st, q, 0u, 0ull, nullptr);
-                else o = sphere_eval(d.radius, q);
-                // torch.argmin (sdf.py:421): smallest value, first index on ties, whatever the visiting order
-                if (bs[k] < 0 || o.val < best[k] || (o.val == best[k] && s < bs[k])) {
-                    best[k] = o.val; bg[k] = o.grad; bs[k] = s;
-                }
+                composed_consider<false>(d, st, s, composed_xform(r0, r1, r2, p[k]), 0u, 0ull, best[k], bg[k], bs[k]);
             }
         };
         for (int si = 0; si < n_sdf; ++si) {
@@ -901,10 +834,7 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
 #pragma unroll
         for (int k = 0; k < kCmPts; ++k) {
             const int sb = max(bs[k], 0);
-            const float4 r0 = sm.xf[lane][3 * sb], r1 = sm.xf[lane][3 * sb + 1], r2 = sm.xf[lane][3 * sb + 2];
-            const f3 go = mk3(fmaf(bg[k].x, r0.x, fmaf(bg[k].y, r1.x, bg[k].z * r2.x)),
-                              fmaf(bg[k].x, r0.y, fmaf(bg[k].y, r1.y, bg[k].z * r2.y)),
-                              fmaf(bg[k].x, r0.z, fmaf(bg[k].y, r1.z, bg[k].z * r2.z)));
+            const f3 go = composed_rotate_back(sm.xf[lane][3 * sb], sm.xf[lane][3 * sb + 1], sm.xf[lane][3 * sb + 2], bg[k]);
             sm.out[lane][warp * kCmPts + k] = make_float4(best[k], go.x, go.y, go.z);
             if (out_which) sm.which[lane][warp * kCmPts + k] = bs[k];
         }

@@ -82,6 +82,39 @@ def winding(desc, points):
     return w
 
 
+def bit_reversed_order(n):
+    """The visiting order the composed kernels use (pvb_kernels.cu fill_order)."""
+    bits = max(0, (n - 1).bit_length())
+    out = []
+    for i in range(1 << bits):
+        r = int(format(i, f"0{bits}b")[::-1], 2) if bits else 0
+        if r < n:
+            out.append(r)
+    return out
+
+
+def composed(descs, xforms, n_cfg, points, order=None, mesh_mode=nat.PVB_MESH_DEFAULT):
+    """(val [n_cfg*P], grad [n_cfg*P,3], which [n_cfg*P]) of the composition of `descs` under xforms
+    [(S*n_cfg),4,4] (sub-SDF-major), visiting the sub-SDFs in `order` (default: the kernels' bit-reversed order)."""
+    p = _pts(points); n = len(p); S = len(descs)
+    arr = (nat.SdfDesc * S)(*descs)
+    xf = np.ascontiguousarray(xforms.detach().cpu().numpy() if torch.is_tensor(xforms) else xforms, dtype=np.float32)
+    assert xf.shape == (S * n_cfg, 4, 4)
+    order = bit_reversed_order(S) if order is None else list(order)
+    assert sorted(order) == list(range(S))
+    od = np.asarray(order, dtype=np.uint8)
+    val, grad = np.empty(n_cfg * n, np.float32), np.empty((n_cfg * n, 3), np.float32)
+    which = np.empty(n_cfg * n, np.int32)
+    lib().sim_composed(arr, ctypes.c_int(S), _p(od), _p(xf), ctypes.c_int(n_cfg), _p(p), ctypes.c_longlong(n),
+                       ctypes.c_uint32(mesh_mode), _p(val), _p(grad), _p(which))
+    return val, grad, which
+
+
+def sphere_desc(radius):
+    import pytorch_volumetric_b200 as pv
+    return pv.SphereSDF(radius).native_desc("cpu")      # the product's own descriptor; no device memory involved
+
+
 def sphere(radius, points):
     p = _pts(points); n = len(p)
     val, grad = np.empty(n, np.float32), np.empty((n, 3), np.float32)

@@ -201,3 +201,97 @@ def test_c1_full_size_drill_grid_vs_oracle(oracle_lib, built_lib):
     assert sign_bad.sum() == 0
     bad_v, bad_g, rep = classify_mesh_mismatch(dist, grad, d_ref, g_ref, TOL, coord_scale=float(np.abs(bb).max()))
     assert bad_v == 0 and bad_g == 0, rep
+
+
+# ---------------------------------------------------------------- ComposedSDF / RobotSDF device logic
+def _close(a, b, tol=1e-5):
+    return np.abs(a - b) <= tol
+
+
+def _composed_golden_descs():
+    zc = golden("ref_cachedsdf_probe")
+    grid, keep = _golden_grid(zc)
+    z = golden("ref_composed")
+    return z, [grid, grid, hs.sphere_desc(float(z["sphere_radius"])), grid], keep
+
+
+def test_composed_logic_vs_reference_golden(built_lib):
+    """composed_xform / composed_consider / composed_rotate_back (the arithmetic of both composed kernels) against
+    the vectors the reference's ComposedSDF produced: plain (S transforms) and configuration-batched (S x A)."""
+    z, descs, keep = _composed_golden_descs()
+    S, A = int(z["S"]), int(z["A"])
+    v, g, w = hs.composed(descs, z["tmat"][:S], 1, z["q"])
+    # an fp32 rigid transform in front of a nearest-voxel lookup flips a few keys at cell boundaries
+    assert (~_close(v, z["val_plain"])).mean() < 2e-3
+    assert (~_close(g, z["grad_plain"]).all(-1)).mean() < 4e-3
+    vb, gb, wb = hs.composed(descs, z["tmat"], A, z["q"])
+    assert (~_close(vb.reshape(A, 30, 100), z["val_batched"])).mean() < 2e-3
+    assert (~_close(gb.reshape(A, 30, 100, 3), z["grad_batched"]).all(-1)).mean() < 4e-3
+    # batched == per-configuration loop, exactly (tests/test_model_to_sdf.py:206-212)
+    tm = z["tmat"].reshape(S, A, 4, 4)
+    for a in range(A):
+        va, ga, wa = hs.composed(descs, np.ascontiguousarray(tm[:, a]), 1, z["q"])
+        sl = slice(a * len(z["q"]), (a + 1) * len(z["q"]))
+        assert np.array_equal(va, vb[sl]) and np.array_equal(ga, gb[sl]) and np.array_equal(wa, wb[sl])
+
+
+def test_composed_result_does_not_depend_on_the_visiting_order(built_lib):
+    """Exact pruning + the explicit first-index tie rule: index order, reversed order and the kernels' bit-reversed
+    order give bit-identical values, gradients and argmin indices -- and equal the unpruned evaluation."""
+    z, descs, keep = _composed_golden_descs()
+    S, A = int(z["S"]), int(z["A"])
+    ref = hs.composed(descs, z["tmat"], A, z["q"], order=range(S))
+    for order in (list(range(S))[::-1], hs.bit_reversed_order(S), [2, 0, 3, 1]):
+        got = hs.composed(descs, z["tmat"], A, z["q"], order=order)
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got)), order
+    # unpruned evaluation: every sub-SDF evaluated alone (a one-element composition never prunes), argmin in numpy
+    per = [hs.composed([descs[s]], z["tmat"][s * A:(s + 1) * A], A, z["q"]) for s in range(S)]
+    vals = np.stack([p[0] for p in per]); grads = np.stack([p[1] for p in per])
+    which = vals.argmin(0)                       # numpy: first index on ties, like torch
+    assert np.array_equal(ref[2], which.astype(np.int32))
+    assert np.array_equal(ref[0], np.take_along_axis(vals, which[None], 0)[0])
+    assert np.array_equal(ref[1], np.take_along_axis(grads, which[None, :, None], 0)[0])
+    # ties: identical sub-SDFs at the same pose resolve to index 0 in every order
+    for n_same in (2, 3, 4, 7):
+        tm = np.repeat(z["tmat"][:1], n_same, axis=0)
+        for order in (range(n_same), list(range(n_same))[::-1], hs.bit_reversed_order(n_same)):
+            _, _, w = hs.composed([descs[0]] * n_same, tm, 1, z["q"], order=order)
+            assert int(w.max()) == 0
+    assert hs.bit_reversed_order(8) == [0, 4, 2, 6, 1, 5, 3, 7] and hs.bit_reversed_order(3) == [0, 2, 1]
+
+
+def test_robot_logic_vs_reference_golden(built_lib):
+    """The reference's RobotSDF vectors (offset_wrench.urdf, 5 configurations): link table + object->link transforms
+    from the golden file through the composed device logic."""
+    z = golden("ref_robot_wrench")
+    shape = tuple(int(s) for s in z["table_shape"])
+    v_, _ = workloads.fixture_mesh("wrench")
+    bb = np.stack([v_.min(0), v_.max(0)], axis=1)
+    grid, keep = hs.grid_desc(torch.from_numpy(z["table_val"]).reshape(shape), torch.from_numpy(z["table_grad"]),
+                              [tuple(r) for r in z["ranges"]], bb)
+    val, grad, _ = hs.composed([grid], z["obj_to_link"], 5, z["q"])
+    assert (~_close(val.reshape(5, -1), z["val"])).mean() < 3e-3
+    assert (~_close(grad.reshape(5, -1, 3), z["grad"]).all(-1)).mean() < 5e-3
+
+
+def test_composed_of_meshes_logic_vs_oracle(oracle_lib, built_lib):
+    """Mesh sub-SDFs (the kMesh instantiation: bounded search radius, sign walk skipped outside a closed mesh's box)
+    against the oracle's ComposedSDF of MeshSDFs, as in tests/test_sdf.py:61-80."""
+    from oracle import port, tp_pytorch_kinematics as opk
+    obj = pv_factory("probe", ray_seed=1)
+    d, keep = hs.mesh_desc(obj)
+    tm = torch.eye(4).repeat(2, 1, 1)
+    tm[0, :3, 3] = torch.tensor([0.1, 0.0, 0.0])
+    tm[1, :3, 3] = torch.tensor([-0.2, 0.0, 0.2])
+    q = workloads.uniform_points(4000, (-0.2, -0.05, -0.1), (0.3, 0.05, 0.3), seed=4)
+    v, g, w = hs.composed([d, d], tm, 1, q)
+    mesh = port_mesh("probe")
+    ref = port.ComposedSDFPort([port.MeshSDFPort(mesh), port.MeshSDFPort(mesh)], opk.Transform3d(matrix=tm))
+    np.random.seed(0)
+    vr, gr = ref(q)
+    assert np.abs(v - vr.numpy()).max() < 1e-5
+    assert (np.abs(g - gr.numpy()).max(-1) > 1e-5).mean() < 2e-3
+    # pruned == unpruned for meshes too
+    per = [hs.composed([d], tm[s:s + 1], 1, q) for s in range(2)]
+    vals = np.stack([p[0] for p in per])
+    assert np.array_equal(w, vals.argmin(0).astype(np.int32)) and np.array_equal(v, vals.min(0))
