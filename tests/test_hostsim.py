@@ -295,3 +295,36 @@ def test_composed_of_meshes_logic_vs_oracle(oracle_lib, built_lib):
     per = [hs.composed([d], tm[s:s + 1], 1, q) for s in range(2)]
     vals = np.stack([p[0] for p in per])
     assert np.array_equal(w, vals.argmin(0).astype(np.int32)) and np.array_equal(v, vals.min(0))
+
+
+def test_closest_point_fuzz_on_degenerate_soups(oracle_lib, built_lib):
+    """BVH4 nearest-first descent + Ericson triangle test of the device code against the oracle's brute force on
+    random triangle soups: coplanar, coincident / duplicated vertices, slivers, far from the origin, zero-area
+    triangles; queries around, near and exactly on the vertices."""
+    import pytorch_volumetric_b200 as pv
+    from oracle import _geom
+    rng = np.random.default_rng(0)
+    for it in range(24):
+        kind = it % 6
+        nv, nf = int(rng.integers(4, 300)), int(rng.integers(1, 600))
+        v = rng.normal(size=(nv, 3)) * 10 ** rng.uniform(-2, 1)
+        if kind == 1: v[:, 2] = 0.0
+        if kind == 2: v = np.round(v, 1)
+        if kind == 3: v[:, 0] *= 1e-3
+        if kind == 4: v += 100.0
+        f = rng.integers(0, nv, size=(nf, 3)).astype(np.int32)
+        if kind == 5: f[:, 2] = f[:, 1]
+        d, keep = hs.mesh_desc(pv.MeshObjectFactory(f"fuzz{it}", mesh=(v, f)))
+        lo, hi = v.min(0), v.max(0)
+        ext = (hi - lo).max() + 1e-3
+        pts = np.concatenate([rng.uniform(lo - 0.3 * ext, hi + 0.3 * ext, size=(1500, 3)),
+                              v[rng.integers(0, nv, 300)] + rng.normal(size=(300, 3)) * 1e-4 * ext,
+                              v[rng.integers(0, nv, 100)]]).astype(np.float32)
+        dist, grad, closest, face = hs.mesh_query(d, pts, mode=0)
+        c_ref = _geom.TriangleSoup(v.astype(np.float32), f).closest_points(pts, method="brute")[0]
+        d_dev = np.linalg.norm(closest.astype(np.float64) - pts, axis=1)
+        d_ref = np.linalg.norm(c_ref.astype(np.float64) - pts, axis=1)
+        scale = max(1.0, float(np.abs(v).max()))
+        assert np.abs(d_dev - d_ref).max() <= 2e-6 * scale, (it, kind)
+        assert (np.abs(np.abs(dist) - d_dev) <= 1e-5 * scale).all() and (dist >= 0).all()      # unsigned mode
+        assert ((face >= 0) & (face < nf)).all()
