@@ -10,7 +10,7 @@ TEST INFRASTRUCTURE.  Two kinds of fixtures:
 2. ref_*.npz -- input/output vectors produced by the UNMODIFIED reference source
    (/root/reference/src/pytorch_volumetric) imported over oracle/shims (the restated third-party
    dependencies).  They pin oracle/port.py (tests/test_oracle_pinning.py) and serve as golden vectors for
-   the CUDA path (tests/test_gpu_golden.py).
+   the CUDA path (tests/test_gpu_mesh.py, test_gpu_cached.py, test_gpu_composed.py, test_gpu_chamfer_sample.py).
 
 Run:  python -m oracle.make_golden
 """
