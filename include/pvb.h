@@ -133,6 +133,14 @@ int pvb_version(void);
 int pvb_sizeof_sdf_desc(void);
 int pvb_sizeof_bvh4_node(void);
 
+/* ---- measurement hook (bench.py's roofline; no reference counterpart) ----
+ * pvb_timing_enable(1): every query entry point below brackets its DOMINANT kernel launch (the tree walk, the
+ * lookup, the composed kernel, the chamfer partial sums) with a pair of CUDA events on the caller's stream.
+ * pvb_timing_last_ms waits for the stop event of the most recent such launch on the current device and returns
+ * that one launch's device time.  Off by default. */
+int pvb_timing_enable(int on);
+int pvb_timing_last_ms(float *ms_out /* HOST */);
+
 /* ---- mesh preprocessing (HOST -> HOST), replaces RaycastingScene construction, sdf.py:115-118 ---- */
 int64_t pvb_bvh_max_nodes(int64_t n_faces);
 /* verts HOST float[n_verts*3], faces HOST int32[n_faces*3];

@@ -94,6 +94,8 @@ _SIGNATURES = {
     "pvb_version": (ctypes.c_int, []),
     "pvb_sizeof_sdf_desc": (ctypes.c_int, []),
     "pvb_sizeof_bvh4_node": (ctypes.c_int, []),
+    "pvb_timing_enable": (ctypes.c_int, [ctypes.c_int]),
+    "pvb_timing_last_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "pvb_bvh_max_nodes": (ctypes.c_int64, [ctypes.c_int64]),
     "pvb_bvh_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
@@ -238,6 +240,18 @@ def deliver(t, device, dtype=None):
         torch.cuda.current_stream(t.device).synchronize()
         return out
     return t.to(device)
+
+
+def timing_enable(on=True):
+    """Bracket the dominant kernel of every query call with CUDA events (include/pvb.h pvb_timing_enable)."""
+    check(lib().pvb_timing_enable(1 if on else 0), "pvb_timing_enable")
+
+
+def timing_last_ms():
+    """Device time (ms) of the most recent dominant-kernel launch on the current device (synchronises on it)."""
+    ms = ctypes.c_float(0.0)
+    check(lib().pvb_timing_last_ms(ctypes.byref(ms)), "pvb_timing_last_ms")
+    return float(ms.value)
 
 
 def bvh_build(verts32, faces32):

@@ -85,15 +85,19 @@ def pairwise_distance_chamfer(A_link_to_world_tfs, B_world_to_link_tfs=None,
                               model_points_eval: torch.tensor = None, vis=None, scale=1000):
     """Chamfer distance of every pairing of two pose sets (reference chamfer.py:20-59).
 
-    Entry [b, p] scores the composite transform B[p] @ A[b] (identity when the two poses agree); B defaults to the
-    inverses of A.  All B*P composites go through one `batch_chamfer_dist` launch.
+    The composites B[p] @ A[b] (identity when the two poses agree; B defaults to the inverses of A) are evaluated in
+    one `batch_chamfer_dist` launch, flat in p-major order.  The reference then returns `errors.view(len(A), len(B))`
+    of that flat data (chamfer.py:49-58), which this function reproduces exactly: for equally sized pose sets -- the
+    only case the reference's callers use -- entry [i, j] scores B[i] @ A[j]; for unequal sizes the view re-chunks
+    the p-major data just like the reference does.
     """
     link_to_world = matrix_of(A_link_to_world_tfs)
     if model_points_eval is None:
         model_points_eval, _, _ = sample_mesh_points(obj_factory, num_points=500, name=obj_factory.name,
                                                      device=link_to_world.device)
     world_to_link = invert_rigid(link_to_world) if B_world_to_link_tfs is None else matrix_of(B_world_to_link_tfs)
-    return _pairwise_chamfer(world_to_link, link_to_world, model_points_eval, obj_factory, obj_sdf, scale, vis)
+    errors = _pairwise_chamfer(world_to_link, link_to_world, model_points_eval, obj_factory, obj_sdf, scale, vis)
+    return errors.reshape(-1).view(link_to_world.shape[0], world_to_link.shape[0])
 
 
 def _pairwise_chamfer(left, right, points, obj_factory, obj_sdf, scale, vis=None):

@@ -44,14 +44,57 @@ static_assert(sizeof(pvb_sdf_desc) % 8 == 0, "descriptor arrays must keep 8-byte
 namespace pvb {
 
 // ------------------------------------------------------------ device info
+// Function attributes and device properties are per device: one process may drive several GPUs (CachedSDF /
+// ComposedSDF accept any device=), so everything cached here is indexed by the current device.
+constexpr int kMaxDevices = 64;
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    static int n[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev] = v;
     }
-    return n;
+    return n[dev];
+}
+
+// Opt-in to > 48 KB of dynamic shared memory for `kernel`, once per (kernel, device).  `slot` is a small per-kernel
+// id; returns false when the runtime refuses.
+enum { kSlotMesh = 0, kSlotGridTma, kSlotCfgMajor, kSlotCfgMajorMulti, kSlotChamfer, kSlotRobot, kSlotRobotMulti,
+       kSlotRobotMc, kSlotCount };
+template <typename K>
+static bool ensure_smem(K kernel, int slot, int bytes) {
+    static unsigned char done[kSlotCount][kMaxDevices] = {{0}};
+    const int dev = current_device();
+    if (done[slot][dev] == 1) return true;
+    const bool ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+    if (ok) done[slot][dev] = 1;
+    return ok;
+}
+
+// ------------------------------------------------------------ kernel timing hook (bench.py roofline)
+// When enabled (pvb_timing_enable), every query entry point brackets its DOMINANT kernel launch with a pair of CUDA
+// events on the caller's stream; pvb_timing_last_ms waits for the stop event and returns the elapsed device time of
+// that one launch.  Off by default: two extra event records per call otherwise.
+static int g_timing = 0;
+static cudaEvent_t g_ev[kMaxDevices][2];
+static unsigned char g_ev_ok[kMaxDevices] = {0};
+static unsigned char g_ev_set[kMaxDevices] = {0};
+static void timing_mark(int which, cudaStream_t stream) {
+    if (!g_timing) return;
+    const int dev = current_device();
+    if (!g_ev_ok[dev]) {
+        if (cudaEventCreate(&g_ev[dev][0]) != cudaSuccess || cudaEventCreate(&g_ev[dev][1]) != cudaSuccess) return;
+        g_ev_ok[dev] = 1;
+    }
+    cudaEventRecord(g_ev[dev][which], stream);
+    if (which == 1) g_ev_set[dev] = 1;
 }
 
 // ------------------------------------------- TMA bulk copy (global -> smem)
@@ -670,7 +713,7 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
                 load_xf(s, r0, r1, r2);
 #pragma unroll
                 for (int k = 0; k < PTS; ++k) {
-                    const uint64_t idx = ((uint64_t)c * (uint64_t)n_pts + (uint64_t)(i0 + k)) * (uint64_t)n_sdf + (uint64_t)s;
+                    const uint64_t idx = ((uint64_t)cfg * (uint64_t)n_pts + (uint64_t)(i0 + k)) * (uint64_t)n_sdf + (uint64_t)s;   // absolute cfg: sharding-independent jitter
                     composed_consider<kMesh>(d, st, s, composed_xform(r0, r1, r2, p[k]), mesh_mode, idx, best[k], bg[k],
                                              bs[k]);
                 }
@@ -1029,18 +1072,32 @@ static int stage_nodes_for(int n_nodes) {
     return n_nodes < max_nodes ? n_nodes : max_nodes;
 }
 
-// kernels that take the staged nodes as dynamic shared memory need the opt-in above 48 KB
-template <typename K>
-static bool allow_big_smem(K kernel) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageNodesMax * 128) ==
-           cudaSuccess;
-}
 
 }  // namespace pvb
 
 using namespace pvb;
 
 // ======================================================================= ABI
+extern "C" int pvb_timing_enable(int on) {
+    g_timing = on ? 1 : 0;
+    return PVB_OK;
+}
+
+extern "C" int pvb_timing_last_ms(float *ms) {
+    if (!ms) { pvb_set_error("pvb_timing_last_ms: null argument"); return PVB_ERR_INVALID; }
+    const int dev = current_device();
+    if (!g_ev_ok[dev] || !g_ev_set[dev]) {
+        pvb_set_error("pvb_timing_last_ms: no timed launch on device %d (call pvb_timing_enable(1) first)", dev);
+        return PVB_ERR_INVALID;
+    }
+    if (cudaEventSynchronize(g_ev[dev][1]) != cudaSuccess ||
+        cudaEventElapsedTime(ms, g_ev[dev][0], g_ev[dev][1]) != cudaSuccess) {
+        pvb_set_error("pvb_timing_last_ms: %s", cudaGetErrorString(cudaGetLastError()));
+        return PVB_ERR_CUDA;
+    }
+    return PVB_OK;
+}
+
 static int check_mesh(const pvb_sdf_desc *m, const char *who) {
     if (!m->nodes || !m->tris || m->n_nodes < 1 || m->n_tris < 1) {
         pvb_set_error("%s: mesh part of the descriptor is empty", who);
@@ -1111,8 +1168,7 @@ extern "C" int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_
     if (n == 0) return PVB_OK;
     const int n_stage = stage_nodes_for(mesh->n_nodes);
     const size_t smem = (size_t)n_stage * 128;
-    static const bool smem_ok = allow_big_smem(mesh_query_kernel);
-    if (!smem_ok) {
+    if (!ensure_smem(mesh_query_kernel, kSlotMesh, kStageNodesMax * 128)) {
         pvb_set_error("pvb_mesh_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
         return PVB_ERR_CUDA;
     }
@@ -1133,9 +1189,11 @@ extern "C" int pvb_mesh_query(const pvb_sdf_desc *mesh, const float *pts, int64_
     }
     // winding mode: unsigned first pass (distance >= 0, gradient away from the surface), sign in a second pass
     const uint32_t walk_mode = winding ? 0u : (mode & ~(uint32_t)PVB_MESH_WINDING);
+    timing_mark(0, (cudaStream_t)stream);
     mesh_query_kernel<<<blocks, kMeshThreads, smem, (cudaStream_t)stream>>>(*mesh, pts, n, perm, (int)run, walk_mode,
                                                                             n_stage, out_dist, out_grad, out_closest,
                                                                             out_face, out_normal);
+    timing_mark(1, (cudaStream_t)stream);
     PVB_CHECK_LAUNCH("pvb_mesh_query");
     if (winding) {
         mesh_winding_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(*mesh, pts, n, perm, mode, out_dist,
@@ -1179,10 +1237,7 @@ extern "C" int pvb_grid_lookup(const pvb_sdf_desc *grid, const float *pts, int64
     long long n_quads = vec_ok ? n / 4 : 0;
     static const int use_tma = [] { const char *e = getenv("PVB_GRID_TMA"); return e ? atoi(e) : 1; }();
     if (use_tma && n_quads >= 4 * kTmaTile && !gt && out_val && out_grad && !out_outside && !out_index) {
-        static const bool smem_ok = cudaFuncSetAttribute(grid_lookup_tma_kernel,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int)sizeof(GridTmaSmem)) == cudaSuccess;
-        if (!smem_ok) {
+        if (!ensure_smem(grid_lookup_tma_kernel, kSlotGridTma, (int)sizeof(GridTmaSmem))) {
             pvb_set_error("pvb_grid_lookup: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
             return PVB_ERR_CUDA;
         }
@@ -1190,16 +1245,20 @@ extern "C" int pvb_grid_lookup(const pvb_sdf_desc *grid, const float *pts, int64
         const long long n_tiles = (4 * n_quads + kTmaTile - 1) / kTmaTile;
         const long long cap = (long long)sm_count() * ctas_per_sm;
         const int blocks = (int)(n_tiles < cap ? n_tiles : cap);
+        timing_mark(0, (cudaStream_t)stream);
         grid_lookup_tma_kernel<<<blocks, kTmaThreads, sizeof(GridTmaSmem), (cudaStream_t)stream>>>(
             *grid, pts, 4 * n_quads, out_val, out_grad);
+        timing_mark(1, (cudaStream_t)stream);
         PVB_CHECK_LAUNCH("pvb_grid_lookup(tma)");
     } else if (n_quads > 0) {
         const int blocks = grid_for(n_quads, kGridThreads, 8);
         auto kern = gt ? grid_lookup_vec4_kernel<true> : grid_lookup_vec4_kernel<false>;
+        timing_mark(0, (cudaStream_t)stream);
         kern<<<blocks, kGridThreads, 0, (cudaStream_t)stream>>>(
             *grid, reinterpret_cast<const float4 *>(pts), n_quads, mesh_mode, reinterpret_cast<float4 *>(out_val),
             reinterpret_cast<float4 *>(out_grad), reinterpret_cast<uchar4 *>(out_outside), surface_level,
             reinterpret_cast<longlong2 *>(out_index));
+        timing_mark(1, (cudaStream_t)stream);
         PVB_CHECK_LAUNCH("pvb_grid_lookup(vec4)");
     }
     const long long first = 4 * n_quads;
@@ -1239,6 +1298,7 @@ static int launch_composed(const pvb_sdf_desc *descs, int n_sdf, const float *xf
     const long long cap = (long long)sm_count() * 64;     // bound the block count for huge configuration batches
     if ((long long)gx * gy > cap) { gy = (int)(cap / gx); if (gy < 1) gy = 1; }
     dim3 grid((unsigned)gx, (unsigned)gy);
+    timing_mark(0, stream);
     if (tg)
         composed_query_kernel<kMesh, PTS, MAXS, true><<<grid, kCompThreads, 0, stream>>>(
             pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, first_pt, n_pts, mesh_mode, nullptr, nullptr,
@@ -1247,6 +1307,7 @@ static int launch_composed(const pvb_sdf_desc *descs, int n_sdf, const float *xf
         composed_query_kernel<kMesh, PTS, MAXS, false><<<grid, kCompThreads, 0, stream>>>(
             pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, first_pt, n_pts, mesh_mode, out_val, out_grad,
             out_which, OutTargets{});
+    timing_mark(1, stream);
     PVB_CHECK_LAUNCH("pvb_composed_query");
     return PVB_OK;
 }
@@ -1290,12 +1351,8 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
     const bool cm_filled = (cfg_count >= 16 && (double)cfg_count >= 0.85 * (double)(cm_tiles * kCmCfg)) ||
                            (tg && tg->vec && cfg_count >= 8);
     if (cfg_major && !needs_mesh && n_sdf <= kCmMaxS && cm_filled) {
-        static const bool smem_ok =
-            cudaFuncSetAttribute(composed_cfgmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(CmSmem)) == cudaSuccess &&
-            cudaFuncSetAttribute(composed_cfgmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(CmSmem)) == cudaSuccess;
-        if (!smem_ok) {
+        if (!ensure_smem(composed_cfgmajor_kernel<false>, kSlotCfgMajor, (int)sizeof(CmSmem)) ||
+            !ensure_smem(composed_cfgmajor_kernel<true>, kSlotCfgMajorMulti, (int)sizeof(CmSmem))) {
             pvb_set_error("pvb_composed_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
             return PVB_ERR_CUDA;
         }
@@ -1308,6 +1365,7 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
         if (gx > n_tiles) gx = n_tiles;
         if (gx < 1) gx = 1;
         dim3 grid((unsigned)gx, (unsigned)gy);
+        timing_mark(0, s);
         if (tg)
             composed_cfgmajor_kernel<true><<<grid, kCmCfg * kCmWarps, sizeof(CmSmem), s>>>(
                 pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, nullptr, nullptr, out_which, *tg);
@@ -1315,6 +1373,7 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
             composed_cfgmajor_kernel<false><<<grid, kCmCfg * kCmWarps, sizeof(CmSmem), s>>>(
                 pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, out_val, out_grad, out_which,
                 OutTargets{});
+        timing_mark(1, s);
         PVB_CHECK_LAUNCH("pvb_composed_query(cfg-major)");
         return PVB_OK;
     }
@@ -1430,8 +1489,7 @@ extern "C" int pvb_chamfer(const pvb_sdf_desc *obj, const float *world_to_object
     }
     const int n_blk = (int)pvb_chamfer_workspace(n_pts);
     const int n_stage = obj->kind == PVB_KIND_MESH ? stage_nodes_for(obj->n_nodes) : 0;
-    static const bool smem_ok = allow_big_smem(chamfer_partial_kernel);
-    if (!smem_ok) {
+    if (!ensure_smem(chamfer_partial_kernel, kSlotChamfer, kStageNodesMax * 128)) {
         pvb_set_error("pvb_chamfer: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
         return PVB_ERR_CUDA;
     }
@@ -1444,8 +1502,10 @@ extern "C" int pvb_chamfer(const pvb_sdf_desc *obj, const float *world_to_object
                                : nullptr;
     if (rc != PVB_OK) return rc;
     dim3 grid((unsigned)n_blk, (unsigned)n_tf);
+    timing_mark(0, (cudaStream_t)stream);
     chamfer_partial_kernel<<<grid, kChamThreads, (size_t)n_stage * 128, (cudaStream_t)stream>>>(
         *obj, world_to_object, pts, n_pts, perm, scale, n_stage, workspace);
+    timing_mark(1, (cudaStream_t)stream);
     PVB_CHECK_LAUNCH("pvb_chamfer(partial)");
     chamfer_finish_kernel<<<n_tf, 32, 0, (cudaStream_t)stream>>>(workspace, n_blk, n_pts, out);
     PVB_CHECK_LAUNCH("pvb_chamfer(finish)");

@@ -80,13 +80,24 @@ class _DeviceSpan:
 
 
 class PeerResult:
-    """One full-size (n_cfg, n_pts) value / gradient buffer per rank, each mapped into every process of the node.
+    """Full-size (n_cfg, n_pts) value / gradient buffers, one pair of SLOTS per rank, each mapped into every process
+    of the node.
 
     Rank r's RobotSDF kernel stores its configuration slab into all `world` buffers (its own and, over NVLink, the
     peers'), so after `publish()` every rank holds the complete result -- the re-assembly SURVEY section 8(e) asks
     for -- without a separate all-gather pass.  Buffers are plain cudaMalloc allocations shared with CUDA IPC
     (pvb_ipc_*); same-node processes only, at most 8 ranks per launch (pvb.h PVB_MAX_TARGETS).
+
+    Ordering.  Two slots alternate per query.  `publish()` (a stream-ordered all-reduce after the kernel) guarantees
+    that every rank's kernel k has finished before anyone reads result k.  The write-after-read hazard -- a fast rank's
+    NEXT kernel storing into a buffer a slow rank is still reading -- is closed by the alternation: query k+2 reuses
+    the slot of query k, and rank A's kernel k+2 follows A's publish k+1, which cannot complete before rank B has
+    entered its own publish k+1, which B's stream orders after everything B enqueued to consume result k.  So the
+    tensors returned for query k stay valid until the same rank issues query k+2 into this PeerResult, provided the
+    consumers are enqueued on the query stream (or synchronised with it) before query k+1 is issued.
     """
+
+    SLOTS = 2
 
     def __init__(self, n_cfg, n_pts, group=None):
         from . import _native as nat
@@ -98,7 +109,8 @@ class PeerResult:
         self.n_cfg, self.n_pts = int(n_cfg), int(n_pts)
         n = self.n_cfg * self.n_pts
         self._grad_offset = (4 * n + 255) // 256 * 256          # value block first, gradient block 256-B aligned
-        self.nbytes = self._grad_offset + 12 * n
+        self._slot_bytes = (self._grad_offset + 12 * n + 255) // 256 * 256
+        self.nbytes = self.SLOTS * self._slot_bytes
         self.device = torch.device("cuda", torch.cuda.current_device())
         self._peer_ptrs = {}
         self._local = ctypes.c_void_p()
@@ -118,18 +130,42 @@ class PeerResult:
                     nat.check(nat.lib().pvb_ipc_open(handles[r], ctypes.byref(mapped)), "pvb_ipc_open")
                     self._peer_ptrs[r] = mapped.value
                     bases[r] = mapped.value
-        self.val = torch.as_tensor(_DeviceSpan(bases[self.rank], n, self), device=self.device).view(self.n_cfg, self.n_pts)
-        self.grad = torch.as_tensor(_DeviceSpan(bases[self.rank] + self._grad_offset, 3 * n, self),
-                                    device=self.device).view(self.n_cfg, self.n_pts, 3)
+        self._bases = bases
         # own buffer first, then the peers in ring order: at any moment the ranks target different destinations
-        order = [(self.rank + k) % self.world for k in range(self.world)]
-        self.targets = [(bases[r], bases[r] + self._grad_offset) for r in order]
+        self._order = [(self.rank + k) % self.world for k in range(self.world)]
+        self._vals, self._grads, self._targets = [], [], []
+        for slot in range(self.SLOTS):
+            off = slot * self._slot_bytes
+            self._vals.append(torch.as_tensor(_DeviceSpan(bases[self.rank] + off, n, self),
+                                              device=self.device).view(self.n_cfg, self.n_pts))
+            self._grads.append(torch.as_tensor(_DeviceSpan(bases[self.rank] + off + self._grad_offset, 3 * n, self),
+                                               device=self.device).view(self.n_cfg, self.n_pts, 3))
+            self._targets.append([(bases[r] + off, bases[r] + off + self._grad_offset) for r in self._order])
+        self._slot = self.SLOTS - 1
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._closed = False
 
+    # the slot of the most recent query
+    @property
+    def val(self):
+        return self._vals[self._slot]
+
+    @property
+    def grad(self):
+        return self._grads[self._slot]
+
+    @property
+    def targets(self):
+        return self._targets[self._slot]
+
+    def next_slot(self):
+        """Advance to the slot the next query writes into; returns its (val, grad) device-address pairs, own first."""
+        self._slot = (self._slot + 1) % self.SLOTS
+        return self._targets[self._slot]
+
     def publish(self):
         """Stream-ordered barrier: when it completes on this rank, every rank's kernel (and with it all of its peer
-        stores) has finished, and no rank starts overwriting before everybody got here."""
+        stores) has finished."""
         if self.world > 1:
             dist.all_reduce(self._flag, group=self.group)
 
@@ -147,7 +183,7 @@ class PeerResult:
             self._peer_ptrs = {}
             if self.world > 1:
                 dist.barrier(group=self.group)
-            self.val = self.grad = None
+            self._vals = self._grads = None
             self.nat.check(self.nat.lib().pvb_ipc_free(self._local), "pvb_ipc_free")
 
 
@@ -157,7 +193,8 @@ def sharded_robot_query(robot_sdf, points, gather=True, group=None, result=None)
     The output slab (cfg_count, P) is a contiguous block of the (|A|, P) result, so re-assembly is a plain
     concatenation on dim 0.  Returns ([A,] *B, N) / (..., 3) when gather=True, else the local slab and its range.
     gather="peer" with a PeerResult: the kernel stores the slab into every rank's buffer directly (no all-gather);
-    the returned tensors are views of `result` and stay valid until the next query into it."""
+    the returned tensors are views of one of `result`'s two slots and stay valid until the second-next query into
+    it (see PeerResult for the cross-rank ordering this relies on)."""
     rank, world = _world(group)
     comp = robot_sdf.sdf
     n_cfg = 1 if comp.tsf_batch is None else math.prod(list(comp.tsf_batch))
@@ -168,7 +205,7 @@ def sharded_robot_query(robot_sdf, points, gather=True, group=None, result=None)
             raise ValueError('gather must be True, False or "peer" (the latter with result=PeerResult(...))')
         if (result.n_cfg, result.n_pts) != (n_cfg, P):
             raise ValueError(f"PeerResult is ({result.n_cfg}, {result.n_pts}), the query is ({n_cfg}, {P})")
-        comp.query_into(points, result.targets, cfg_begin=begin, cfg_count=end - begin)
+        comp.query_into(points, result.next_slot(), cfg_begin=begin, cfg_count=end - begin)
         result.publish()
         lead = tuple(points.shape[:-1])
         batch = tuple(comp.tsf_batch) if comp.tsf_batch is not None else ()

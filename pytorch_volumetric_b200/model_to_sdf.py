@@ -62,6 +62,8 @@ class RobotSDF(sdf.ObjectFrameSDF):
         # visual origin of every mesh inside its link frame, stacked link-major
         self.offset_transforms = Transform3d(
             matrix=torch.cat([matrix_of(vis.offset) for _, vis in visuals]).to(device=self.device, dtype=self.dtype))
+        # inverse of the visual offsets, once (general inverse: a scaled <visual><origin> is not rigid)
+        self._mesh_from_link = self.offset_transforms.inverse().get_matrix()
         self.sdf: typing.Optional[sdf.ComposedSDF] = sdf.ComposedSDF(link_sdfs, None)
         self.set_joint_configuration(default_joint_config)
 
@@ -80,7 +82,7 @@ class RobotSDF(sdf.ObjectFrameSDF):
         poses = self.chain.forward_kinematics(flat_q, end_only=False)
         world_from_link = torch.stack([matrix_of(poses[name]) for name in self.sdf_to_link_name])   # (S, |A|, 4, 4)
         n_links, n_cfg = world_from_link.shape[:2]
-        mesh_from_link = invert_rigid(matrix_of(self.offset_transforms)).to(world_from_link)        # (S, 4, 4)
+        mesh_from_link = self._mesh_from_link.to(world_from_link)                                   # (S, 4, 4)
         # base frame -> mesh frame of each link: (FK @ visual_offset)^-1, link-major like the reference's stack
         mesh_from_world = mesh_from_link[:, None] @ invert_rigid(world_from_link)
         self.object_to_link_frames = Transform3d(matrix=mesh_from_world.reshape(n_links * n_cfg, 4, 4))
@@ -97,7 +99,7 @@ class RobotSDF(sdf.ObjectFrameSDF):
 
     def link_bounding_boxes(self):
         """Corner points (8 x 3, robot frame) of every link's box under the installed configuration(s)."""
-        world_from_mesh = Transform3d(matrix=invert_rigid(matrix_of(self.sdf.obj_frame_to_link_frame)))
+        world_from_mesh = Transform3d(matrix=sdf._affine_inverse(matrix_of(self.sdf.obj_frame_to_link_frame)))
         per_link = []
         for i, link_sdf in enumerate(self.sdf.sdfs):
             corners = aabb_to_ordered_end_points(np.asarray(link_sdf.surface_bounding_box(padding=0)))

@@ -126,7 +126,16 @@ class Transform3d:
         return Transform3d(matrix=m)
 
     def inverse(self, invert_composed=False):
-        return Transform3d(matrix=invert_rigid(self._m))
+        """General inverse, as pk's Transform3d.inverse: the closed form [R^T | -R^T t] when every 3x3 block is
+        orthonormal (the rigid case, exact transposes), torch.linalg.inv otherwise (scaled visual offsets,
+        user-supplied affines)."""
+        m = self._m
+        R = m[:, :3, :3]
+        eye = torch.eye(3, dtype=m.dtype, device=m.device)
+        tol = 1e-5 if m.dtype == torch.float32 else 1e-10
+        rigid = bool(((R @ R.transpose(-1, -2) - eye).abs().amax() < tol).item()) and \
+            bool((m[:, 3, :3].abs().amax() == 0).item()) and bool(((m[:, 3, 3] - 1).abs().amax() == 0).item())
+        return Transform3d(matrix=invert_rigid(m) if rigid else torch.linalg.inv(m))
 
     def stack(self, *others):
         return Transform3d(matrix=torch.cat([self._m] + [matrix_of(o) for o in others], dim=0))
