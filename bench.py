@@ -1,18 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- SDF+grad queries/s of the batched signed-distance query path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]
-                    [--workload c2|mesh10k|mesh50k|c3|c3cached|c4|c4gather|c4peer|c4readme|c5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload default|c4|c2|mesh10k|mesh50k|c3|c3cached|c5|c4readme]
+                    [--impl reference]
 
-One "step" = one pass of the hot path over one batch of synthetic input.  The default workload is BASELINE.json
-configs[1] (C2): CachedSDF(res=0.005) of the YCB drill, 10^7 random query points (42 % out of range), value +
-gradient.  With N > 1 (torchrun, one rank per GPU) every rank runs the same per-GPU batch on its own seeded points
-(weak scaling; the path partitions over independent points / configurations, so there is no data-path collective);
-`value` is the whole-job aggregate over the max-over-ranks device time.
+One "step" = one pass of the hot path over one batch of synthetic input.
 
-`--impl reference` times the CPU restatement of the reference (oracle/port.py, torch-cpu, all host threads) on a
-bounded sample of the same workload; the reference itself is pure Python over third-party wheels that are not
-installable in this image, so the oracle port is the reference arm.
+DEFAULT (no --workload): the line the driver records.
+  * headline = BASELINE.json configs[3] (C4), the workload north_star's multi-GPU target names: RobotSDF of a
+    7-DOF arm (8 link SDFs), 200 joint configurations x 100 000 query points, value + gradient.  With N > 1
+    (torchrun, one rank per GPU) the CONFIGURATION batch is split over the ranks (strong scaling: total work fixed)
+    and the timed step ends with the FULL (200, 100 000) result on EVERY rank -- re-assembly inside the timed
+    region.  `value` = 2*10^7 (configuration, point) pairs / max-over-ranks device time.  The `reassembly` object
+    carries the sub-values next to it: no_reassembly (every rank keeps its slab), nccl_all_gather, peer_stores
+    (kernel epilogue stores into all ranks' buffers over NVLink), each timed the same way.
+  * `workloads`: every other BASELINE config on the same GPUs in the same run -- mesh10k (the north-star
+    single-GPU target: MeshSDF on a 10 000-triangle mesh, 10^7 queries), c2, c3, c3cached, c5 -- each with value,
+    ms_per_step, roofline{achieved, frac, traffic, kernel_ms}, e2e and (N=1) cpu_baseline.
+
+`roofline.kernel_ms` is an independent measurement: the library brackets the dominant kernel launch of one call with
+its own pair of CUDA events on the launch stream (pvb_timing_enable / pvb_timing_last_ms); median of 7 launches.
+`roofline.traffic` is the ncu dram__bytes_read+write of that kernel from the committed capture (profiles/ncu_traffic.json).
+
+`--impl reference` times the CPU restatement of the reference (oracle/port.py, torch-cpu + OpenMP BVH, all host
+threads that help) on a bounded sample of the same workloads; the reference itself is pure Python over third-party
+wheels that are not installable in this image, so the oracle port is the reference arm.
 
 Prints ONE JSON line (rank 0).
 """
@@ -34,6 +46,8 @@ import workloads  # noqa: E402
 
 METRIC = "sdf_grad_queries_per_s"
 UNIT = "queries/s"
+HEADLINE = "c4"
+OTHER_WORKLOADS = ("mesh10k", "c2", "c3", "c3cached", "c5")
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -273,58 +287,109 @@ class Mesh10k(Workload):
         return self.cpu_sample
 
 
+def c4_config(n_cfg=200, n_pts=100_000):
+    """The `config` object of the headline, IDENTICAL in the GPU arm and the reference arm."""
+    return {"workload": f"C4 RobotSDF synthetic 7-DOF arm (8 links, per-link CachedSDF res=0.02 pad=1.0) x {n_cfg} joint "
+                        f"configurations x {n_pts} uniform points, value+gradient; configurations sharded over the "
+                        f"ranks, full ({n_cfg}, {n_pts}) result on every rank inside the timed region",
+            "n_cfg": n_cfg, "n_pts": n_pts, "units_per_step": n_cfg * n_pts,
+            "l2_policy": "output 320 MB/step > L2 (126 MB); 3 rotating point buffers",
+            "result_reassembly": "full result on every rank; method = the faster of NCCL all-gather / peer stores "
+                                 "measured in this run (reassembly.chosen); no collective at N=1"}
+
+
 class C4(Workload):
     """BASELINE C4: RobotSDF, synthetic iiwa-like 7-DOF arm (8 link meshes), per-link CachedSDF(res 0.02, padding
-    1.0), 200 joint configurations x 100 000 points; with N GPUs the configuration batch is sharded (strong
-    scaling is reported by the driver from the per-N lines; per-GPU work = 200/N configurations)."""
+    1.0), 200 joint configurations x 100 000 points.  With N GPUs the configuration batch is split into contiguous
+    slabs (strong scaling); `mode` selects what a step leaves behind: "none" (every rank keeps its slab), "nccl"
+    (all-gather of the slabs), "peer" (the kernel epilogue stores each slab into all ranks' buffers)."""
     name = "c4"
     kernel = "composed_cfgmajor_kernel | composed_query_kernel<false,2,16> (by configuration-tile fill)"
 
-    def __init__(self, rank, world=1, n_cfg=200, n_pts=100_000, cache_dir=None, gather=False):
+    def __init__(self, rank, world=1, n_cfg=200, n_pts=100_000, cache_dir=None, mode="none"):
         import pytorch_volumetric_b200 as pv
         from pytorch_volumetric_b200 import distributed as pd
-        self.gather = gather if world > 1 else False
-        self.pd = pd
-        self.peer = pd.PeerResult(n_cfg, n_pts) if self.gather == "peer" else None
+        self.pv, self.pd = pv, pd
+        self.rank, self.world = rank, world
+        self.mode = mode if world > 1 else "none"
+        self.peer = None
+        self.peer_error = None
         d = os.path.join(cache_dir or tempfile.gettempdir(), f"pvb_bench_arm_{rank}")
         urdf, end = workloads.write_arm(d)
         chain = pv.build_serial_chain_from_urdf(open(urdf).read(), end).to(device="cuda")
         self.robot = pv.RobotSDF(chain, path_prefix=d,
                                  link_sdf_cls=pv.cache_link_sdf_factory(resolution=0.02, padding=1.0, device="cuda",
                                                                         cache_path=os.path.join(d, "cache.pkl")))
-        self.th = workloads.arm_configurations(n_cfg).cuda()
+        self.th_host = workloads.arm_configurations(n_cfg).pin_memory()
+        self.th = self.th_host.cuda()
         self.robot.set_joint_configuration(self.th)
         lo = [r[0] for r in workloads.ARM_QUERY_RANGE]; hi = [r[1] for r in workloads.ARM_QUERY_RANGE]
         self.host = [workloads.uniform_points(n_pts, lo, hi, seed=4 + b).pin_memory() for b in range(3)]
         self.dev = [h.cuda() for h in self.host]
         self.begin, self.end = pd.shard_range(n_cfg, rank, world)
         self.n_pts, self.n_cfg = n_pts, n_cfg
-        self.units = (self.end - self.begin) * n_pts
+        self.units = (self.end - self.begin) * n_pts           # pairs this rank evaluates per step
         n_vox = sum(int(np.prod(s.voxels.shape)) for s in self.robot.sdf.sdfs)
         self.n_vox = n_vox
-        self.alg_bytes = 16 * self.units + 12 * n_pts + 64 * 8 * (self.end - self.begin) + 16 * n_vox
-        self.h2d_bytes = 12 * n_pts
+        # SURVEY 8(d): 16 B per (configuration, point) pair out + points + transforms + tables once per launch
+        self.alg_bytes = 16 * self.units + 12 * n_pts + 48 * 8 * (self.end - self.begin) + 16 * n_vox
+        self.h2d_bytes = 12 * n_pts + 4 * 7 * (self.end - self.begin)
         self.d2h_bytes = 16 * self.units
         self.launches_per_step = 1
-        self.desc = {"workload": f"C4 RobotSDF synthetic 7-DOF arm (8 links, CachedSDF res=0.02 pad=1.0, "
-                                 f"{n_vox} voxels = {16 * n_vox / 1e6:.0f} MB tables) x {n_cfg} configurations x "
-                                 f"{n_pts} points, configurations sharded over ranks",
-                     "configs_this_rank": self.end - self.begin, "l2_policy": "output 320 MB/step > L2",
-                     "result_reassembly": {True: "all-gather of the per-rank slabs (NCCL)",
-                                           "peer": "kernel epilogue stores every slab into all ranks' buffers over "
-                                                   "NVLink (peer-mapped, CUDA IPC) + one 4-byte all-reduce as barrier",
-                                           False: "none: every rank keeps its configuration slab"}[self.gather]}
+        self.desc = c4_config(n_cfg, n_pts) if (n_cfg, n_pts) == (200, 100_000) else \
+            {"workload": f"RobotSDF synthetic 7-DOF arm x {n_cfg} configurations x {n_pts} points"}
+
+    def enable_peer(self):
+        """Allocate + map the peer result buffers (collective).  Returns None or the reason it is unavailable."""
+        if self.world == 1 or self.peer is not None:
+            return None
+        try:
+            self.peer = self.pd.PeerResult(self.n_cfg, self.n_pts)
+        except Exception as e:        # no peer access between these GPUs, IPC refused, ...
+            self.peer_error = repr(e)[:300]
+        # all ranks must agree
+        ok = torch.tensor([0.0 if self.peer is None else 1.0], device="cuda")
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        if ok.item() == 0.0 and self.peer is not None:
+            self.peer.close()
+            self.peer = None
+            self.peer_error = self.peer_error or "another rank could not map the peer buffers"
+        elif ok.item() == 0.0:
+            torch.distributed.barrier()
+        return self.peer_error
+
+    def set_mode(self, mode):
+        self.mode = mode if self.world > 1 else "none"
 
     def step(self, i):
-        if self.gather == "peer":   # full result on every rank, written by the kernels themselves
-            return self.pd.sharded_robot_query(self.robot, self.dev[i % 3], gather="peer", result=self.peer)
-        if self.gather:      # every rank ends up with the full (200, M) result: one NCCL all-gather per tensor
-            return self.pd.sharded_robot_query(self.robot, self.dev[i % 3], gather=True)
-        return self.robot.sdf.query(self.dev[i % 3], cfg_begin=self.begin, cfg_count=self.end - self.begin)
+        pts = self.dev[i % 3]
+        if self.world == 1:
+            return self.robot(pts)                                 # the public RobotSDF.__call__
+        if self.mode == "peer":   # full result on every rank, written by the kernels themselves
+            return self.pd.sharded_robot_query(self.robot, pts, gather="peer", result=self.peer)
+        if self.mode == "nccl":   # full result on every rank: one NCCL all-gather per tensor
+            return self.pd.sharded_robot_query(self.robot, pts, gather=True)
+        return self.pd.sharded_robot_query(self.robot, pts, gather=False)
+
+    def step_reconfigure(self, i):
+        """set_joint_configuration (FK + link-frame composition) + the query, through the public RobotSDF API."""
+        self.robot.set_joint_configuration(self.th)
+        return self.step(i)
 
     def step_host(self, i):
-        v, g = self.robot.sdf.query(self.host[i % 3], cfg_begin=self.begin, cfg_count=self.end - self.begin)
-        return v.cpu(), g.cpu()
+        """Public API end to end: host joint values + host points in, this rank's slab of the result in pinned host
+        memory out (the union over ranks is the full result)."""
+        self.robot.set_joint_configuration(self.th_host[self.begin:self.end].to("cuda", non_blocking=True))
+        out = self.robot(self.host[i % 3])
+        return out
+
+    def restore(self):
+        self.robot.set_joint_configuration(self.th)
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
 
 class C5(Workload):
@@ -419,10 +484,6 @@ def make_workload(name, rank, world):
         return Mesh10k(rank, n_lon=250, n_lat=101)
     if name == "c4":
         return C4(rank, world)
-    if name == "c4gather":
-        return C4(rank, world, gather=True)
-    if name == "c4peer":
-        return C4(rank, world, gather="peer")
     if name == "c4readme":
         return C4(rank, world, n_cfg=200, n_pts=15251)
     if name == "c5":
@@ -432,6 +493,9 @@ def make_workload(name, rank, world):
     if name == "c3cached":
         return C3(rank, world, cached=True)
     raise SystemExit(f"unknown workload {name}")
+
+
+WEAK_SCALED = ("c2", "mesh10k", "mesh50k")       # every rank runs the full batch on its own points
 
 
 # ------------------------------------------------------------------------------------------- reference arm
@@ -481,7 +545,7 @@ def cpu_arm(name):
                       "uniform points of the [-0.7, 0.7]^3 query box x 16 sub-SDFs; oracle/port.py ComposedSDFPort "
                       "(sdf.py:392-433 restated: per-SDF loop + argmin)",
                       f"C3 ComposedSDF of 16 drills ({'CachedSDF res=0.005' if name == 'c3cached' else 'MeshSDF'})")
-    if name in ("c4", "c4gather", "c4peer", "c4readme"):
+    if name in ("c4", "c4readme"):
         d = os.path.join(tempfile.gettempdir(), "pvb_bench_arm_cpu")
         urdf, end = workloads.write_arm(d)
         chain = opk.build_serial_chain_from_urdf(open(urdf).read(), end)
@@ -552,154 +616,62 @@ def pick_cpu_threads(probe):
     return best, tried
 
 
-REFERENCE_ARM_BUDGET_S = 150.0      # the whole --impl reference run (warm-up + timed steps) is sized to about this
+# headline of the --impl reference run (warm-up + timed steps) is sized to about this many seconds, each entry of its
+# `workloads` object to about the second figure (PVB_BENCH_REF_BUDGET_S: the CPU test tier shortens both)
+REFERENCE_ARM_BUDGET_S = float(os.environ.get("PVB_BENCH_REF_BUDGET_S", 120.0))
+REFERENCE_OTHER_BUDGET_S = min(6.0, REFERENCE_ARM_BUDGET_S)
+
+
+def _time_cpu_arm(arm, steps, warmup, budget_s):
+    """Bounded sample of one CPU arm: thread count = the fastest on this host, step size from a throughput probe so
+    that warm-up + `steps` steps take about `budget_s`.  Returns the cpu_baseline-style dict + ms per step."""
+    probe = max(1000, arm.max_n // 20)
+    cores, tried = pick_cpu_threads(lambda: arm.run(probe))
+    t0 = time.perf_counter()
+    arm.run(probe)
+    per_point = (time.perf_counter() - t0) / probe
+    n = int(budget_s / (steps + max(warmup, 1)) / per_point)
+    n = max(1000, min(arm.max_n, n))
+    sample = n * arm.units_per_point
+    for _ in range(max(warmup, 1)):
+        arm.run(n)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        arm.run(n)
+    dt = time.perf_counter() - t0
+    what = (f"{n} points per step ({sample} units); {arm.what}; {cores} host threads = the fastest of "
+            f"{sorted(tried)} tried on {usable_cpus()} usable CPUs")
+    return {"value": sample * steps / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": what}, 1e3 * dt / steps
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    arm = cpu_arm(args.workload)
-    probe = max(1000, arm.max_n // 20)
-    cores, tried = pick_cpu_threads(lambda: arm.run(probe))
-    # bounded sample: measure the host's throughput on a small slice, then size one step so that K + W of them fit
-    # the budget (never more than the arm's full sample)
-    t0 = time.perf_counter()
-    arm.run(probe)
-    per_point = (time.perf_counter() - t0) / probe
-    n = int(REFERENCE_ARM_BUDGET_S / (args.steps + max(args.warmup, 1)) / per_point)
-    n = max(1000, min(arm.max_n, n))
-    sample = n * arm.units_per_point
-    fn = lambda: arm.run(n)         # noqa: E731
-    wl = arm.label
-    what = (f"{n} points per step ({sample} units); {arm.what}; {cores} host threads = the fastest of "
-            f"{sorted(tried)} tried on {usable_cpus()} usable CPUs")
-    for _ in range(max(args.warmup, 1)):
-        fn()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fn()
-    dt = time.perf_counter() - t0
-    val = sample * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl, "sample_units_per_step": sample},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": what},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    name = HEADLINE if args.workload == "default" else args.workload
+    arm = cpu_arm(name)
+    cpu, ms = _time_cpu_arm(arm, args.steps, args.warmup, REFERENCE_ARM_BUDGET_S)
+    config = c4_config() if name == "c4" else {"workload": arm.label}
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong" if name not in WEAK_SCALED else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.workload == "default":
+        others = {}
+        for w in OTHER_WORKLOADS:
+            try:
+                c, ms_w = _time_cpu_arm(cpu_arm(w), 2, 1, REFERENCE_OTHER_BUDGET_S)
+                others[w] = {"value": c["value"], "unit": UNIT, "ms_per_step": ms_w, "cpu_baseline": c}
+            except Exception as e:      # never lose the headline to a secondary arm
+                others[w] = {"error": repr(e)[:200]}
+        line["workloads"] = others
     print(json.dumps(line))
     return 0
 
 
-# -------------------------------------------------------------------------------------------------- main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="c2")
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
-    if args.impl == "reference":
-        return run_reference(args)
-
-    rank, world, local = dist_setup(args.gpus)
-    from pytorch_volumetric_b200 import _native
-    if _native.lib_missing() and rank == 0:      # normally prebuilt by __graft_entry__.build(); the product never builds itself
-        _native.build()
-    barrier(world)
-    sampler = ClockSampler(local)
-    wl = make_workload(args.workload, rank, world)
-    torch.cuda.synchronize()
-
-    # ---- device-resident arm (value) ----
-    out = None
-    for i in range(args.warmup):         # same ownership pattern as the timed loop (the previous result stays alive
-        out = wl.step(i)                 # while the next one is allocated), so the allocator is in steady state
-    stream = torch.cuda.current_stream()
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier(world)
-    sampler.start()
-    t_cpu0 = time.perf_counter()
-    t_begin.record(stream)
-    for i in range(args.steps):          # nothing but the public API call in the timed loop
-        out = wl.step(i)
-    t_end.record(stream)
-    cpu_issue_us = (time.perf_counter() - t_cpu0) / args.steps * 1e6
-    sampler.sample_now()                 # the GPU is still executing the queued timed steps here
-    barrier(world)
-    clocks = sampler.stop()
-    total_ms = max_over_ranks(t_begin.elapsed_time(t_end), world)
-    # device time per launch of the dominant kernel: the timed region is K back-to-back steps on one stream,
-    # bracketed by CUDA events on that stream
-    kernel_ms = t_begin.elapsed_time(t_end) / args.steps
-    units_all = max_over_ranks(float(wl.units), world) * world if args.workload in ("c2", "mesh10k", "mesh50k") \
-        else sum_over_ranks(float(wl.units), world)
-    value = units_all * args.steps / (total_ms * 1e-3)
-    del out
-
-    # ---- end-to-end arm: host buffers through the public API, H2D + D2H inside the timed region ----
-    e2e = None
-    if not args.no_e2e:
-        e2e_steps = max(3, min(args.steps, 10))
-        r = None
-        for i in range(3):               # steady state of the pinned host allocator, see above
-            r = wl.step_host(i)
-        barrier(world)
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            r = wl.step_host(i)
-        torch.cuda.synchronize()
-        barrier(world)
-        dt = max_over_ranks(time.perf_counter() - t0, world)
-        e2e = {"value": units_all * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
-               "d2h_bytes_per_step": wl.d2h_bytes, "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps}
-        del r
-
-    # ---- roofline of the dominant kernel ----
-    peak, peak_kind = measured_peaks()
-    achieved = wl.alg_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(wl.name), "kernel": wl.kernel, "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_launch": wl.alg_bytes, "peak_source": f"of {peak_kind}"}
-
-    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        if hasattr(wl, "cpu_setup"):        # same tables / points as the GPU arm
-            sample = wl.cpu_setup()
-            cpu_step = wl.cpu_step
-        else:
-            arm = cpu_arm(args.workload)
-            sample = f"{arm.max_n} points per step; {arm.what}"
-            cpu_step = lambda: (arm.run(arm.max_n), arm.max_n * arm.units_per_point)[1]      # noqa: E731
-        cpu_threads, tried = pick_cpu_threads(cpu_step)
-        sample += f"; {cpu_threads} host threads = the fastest of {sorted(tried)} tried"
-        t0 = time.perf_counter()
-        done = 0
-        while time.perf_counter() - t0 < 8.0:
-            done += cpu_step()
-        dt = time.perf_counter() - t0
-        cpu = {"value": done / dt, "unit": UNIT, "cores": cpu_threads, "kind": "port", "sample": sample}
-
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak" if args.workload in ("c2", "mesh10k", "mesh50k") else "strong",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.desc, "clocks": clocks,
-                "e2e": e2e, "gpu_launches": wl.launches_per_step * args.steps, "roofline": roofline,
-                "host_issue_us_per_step": cpu_issue_us,
-                "cpu_baseline": cpu}
-        print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
-    return 0
-
-
+# ------------------------------------------------------------------------------------------------ GPU arms
 def sum_over_ranks(x, world):
     if world > 1:
         import torch.distributed as dist
@@ -707,6 +679,279 @@ def sum_over_ranks(x, world):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
     return x
+
+
+def timed_steps(step, steps, warmup, world, sampler=None):
+    """`warmup` untimed steps, then exactly `steps` steps bracketed by barrier + synchronize on both sides, timed with
+    CUDA events on the launch stream; returns (max-over-ranks ms for all steps, this rank's ms, host issue us/step)."""
+    out = None
+    for i in range(warmup):             # same ownership pattern as the timed loop (the previous result stays alive
+        out = step(i)                   # while the next one is allocated), so the allocator is in steady state
+    stream = torch.cuda.current_stream()
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    if sampler is not None:
+        sampler.start()
+    t_cpu0 = time.perf_counter()
+    t_begin.record(stream)
+    for i in range(steps):              # nothing but the public API call in the timed loop
+        out = step(i)
+    t_end.record(stream)
+    issue_us = (time.perf_counter() - t_cpu0) / steps * 1e6
+    if sampler is not None:
+        sampler.sample_now()            # the GPU is still executing the queued timed steps here
+    barrier(world)
+    mine = t_begin.elapsed_time(t_end)
+    del out
+    return max_over_ranks(mine, world), mine, issue_us
+
+
+def kernel_time_ms(step, n=7):
+    """Device time of ONE launch of the workload's dominant kernel, measured by the library's own event pair around
+    that launch (median of n calls, each followed by a synchronize): independent of ms_per_step."""
+    from pytorch_volumetric_b200 import _native
+    _native.timing_enable(True)
+    ts = []
+    try:
+        for i in range(n):
+            out = step(i)
+            ts.append(_native.timing_last_ms())
+            torch.cuda.synchronize()
+            del out
+    finally:
+        _native.timing_enable(False)
+    return statistics.median(ts)
+
+
+def e2e_arm(wl, units_all, world, steps):
+    """Host buffers through the public API, H2D + D2H inside the timed region (wall clock around a synchronize,
+    max over ranks)."""
+    r = None
+    for i in range(3):                  # steady state of the pinned host allocator
+        r = wl.step_host(i)
+    torch.cuda.synchronize()
+    barrier(world)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        r = wl.step_host(i)
+    torch.cuda.synchronize()
+    dt_mine = time.perf_counter() - t0
+    barrier(world)
+    dt = max_over_ranks(dt_mine, world)
+    del r
+    return {"value": units_all * steps / dt, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
+            "d2h_bytes_per_step": wl.d2h_bytes, "ms_per_step": 1e3 * dt / steps, "steps": steps}
+
+
+def roofline_of(wl, kernel_ms):
+    peak, peak_kind = measured_peaks()
+    achieved = wl.alg_bytes / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(wl.name), "kernel": wl.kernel, "kernel_ms": kernel_ms,
+            "algorithmic_bytes_per_launch": wl.alg_bytes, "peak_source": f"of {peak_kind}"}
+
+
+class all_host_cpus:
+    """The CPU arm may use every core the process was started with, not only the GPU's NUMA node; the NUMA binding
+    is put back afterwards so that later pinned buffers stay local."""
+
+    def __init__(self, full_affinity):
+        self.full = full_affinity
+
+    def __enter__(self):
+        self.bound = os.sched_getaffinity(0) if self.full is not None else None
+        if self.full is not None:
+            os.sched_setaffinity(0, self.full)
+
+    def __exit__(self, *exc):
+        if self.bound is not None:
+            os.sched_setaffinity(0, self.bound)
+        return False
+
+
+def cpu_baseline_of(name, wl=None, seconds=6.0):
+    """Oracle port of one workload on the host cores, bounded sample (rank 0, N=1 only)."""
+    if wl is not None and hasattr(wl, "cpu_setup"):          # same tables / points as the GPU arm
+        sample = wl.cpu_setup()
+        cpu_step = wl.cpu_step
+    else:
+        arm = cpu_arm(name)
+        n = max(1000, arm.max_n // 4)
+        sample = f"{n} points per step; {arm.what}"
+        cpu_step = lambda: (arm.run(n), n * arm.units_per_point)[1]      # noqa: E731
+    cpu_threads, tried = pick_cpu_threads(cpu_step)
+    sample += f"; {cpu_threads} host threads = the fastest of {sorted(tried)} tried"
+    t0 = time.perf_counter()
+    done = 0
+    while time.perf_counter() - t0 < seconds:
+        done += cpu_step()
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": cpu_threads, "kind": "port", "sample": sample}
+
+
+def run_workload(name, rank, world, steps, warmup, with_e2e, with_cpu, sampler=None, full_affinity=None):
+    """One non-headline workload: device-resident value, independent kernel time + roofline, e2e, CPU baseline."""
+    wl = make_workload(name, rank, world)
+    torch.cuda.synchronize()
+    total_ms, _, issue_us = timed_steps(wl.step, steps, warmup, world, sampler)
+    units_all = max_over_ranks(float(wl.units), world) * world if name in WEAK_SCALED \
+        else sum_over_ranks(float(wl.units), world)
+    res = {"value": units_all * steps / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / steps,
+           "steps": steps, "scaling": "weak" if name in WEAK_SCALED else "strong", "config": wl.desc,
+           "gpu_launches": wl.launches_per_step * steps, "host_issue_us_per_step": issue_us}
+    res["roofline"] = roofline_of(wl, kernel_time_ms(wl.step))
+    if with_e2e:
+        res["e2e"] = e2e_arm(wl, units_all, world, max(3, min(steps, 10)))
+    if with_cpu:
+        with all_host_cpus(full_affinity):
+            res["cpu_baseline"] = cpu_baseline_of(name, wl)
+    return wl, res
+
+
+# -------------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="default")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="default run: headline only")
+    ap.add_argument("--mode", default=None, choices=[None, "none", "nccl", "peer"],
+                    help="C4 at N>1: force the re-assembly method of the headline instead of picking the faster one")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = dist_setup(args.gpus)
+    from pytorch_volumetric_b200 import _native
+    from pytorch_volumetric_b200 import distributed as pd
+    if _native.lib_missing() and rank == 0:      # normally prebuilt by __graft_entry__.build(); the product never builds itself
+        _native.build()
+    # pin the rank next to its GPU before any pinned host buffer exists (e2e across the box, VERDICT r01 item 6)
+    bound = pd.bind_to_gpu_numa_node(local)
+    full_affinity = bound[2] if bound else None
+    barrier(world)
+    sampler = ClockSampler(local)
+    with_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+
+    if args.workload != "default" and args.workload not in ("c4", "c4readme"):
+        # ---- single-workload mode (tuning / profiling scripts) ----
+        wl, res = run_workload(args.workload, rank, world, args.steps, args.warmup, not args.no_e2e, with_cpu,
+                               sampler, full_affinity)
+        clocks = sampler.stop()
+        if rank == 0:
+            line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                    "scaling": res["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": wl.desc, "clocks": clocks, "e2e": res.get("e2e"), "gpu_launches": res["gpu_launches"],
+                    "roofline": res["roofline"], "host_issue_us_per_step": res["host_issue_us_per_step"],
+                    "cpu_baseline": res.get("cpu_baseline")}
+            print(json.dumps(line))
+        return finish(world)
+
+    # ---- headline: C4 RobotSDF, configurations split over the ranks, full result on every rank ----
+    wl = make_workload("c4" if args.workload == "default" else args.workload, rank, world)
+    torch.cuda.synchronize()
+    units_all = sum_over_ranks(float(wl.units), world)
+    sub_steps = max(5, min(args.steps, 20))
+    reassembly = None
+    if world > 1:
+        reassembly = {}
+        wl.set_mode("none")
+        ms, _, _ = timed_steps(wl.step, sub_steps, args.warmup, world)
+        reassembly["no_reassembly"] = {"ms_per_step": ms / sub_steps, "value": units_all * sub_steps / (ms * 1e-3)}
+        wl.set_mode("nccl")
+        ms, _, _ = timed_steps(wl.step, sub_steps, args.warmup, world)
+        reassembly["nccl_all_gather"] = {"ms_per_step": ms / sub_steps, "value": units_all * sub_steps / (ms * 1e-3)}
+        err = wl.enable_peer()
+        if err is None:
+            wl.set_mode("peer")
+            ms, _, _ = timed_steps(wl.step, sub_steps, args.warmup, world)
+            remote = 16.0 * wl.units * (world - 1)          # bytes this rank pushes to its peers per step
+            reassembly["peer_stores"] = {"ms_per_step": ms / sub_steps, "value": units_all * sub_steps / (ms * 1e-3),
+                                         "nvlink_out_GBps_per_rank": remote / (ms / sub_steps * 1e-3) / 1e9,
+                                         "nvlink_in_bytes_per_rank": remote}
+        else:
+            reassembly["peer_stores"] = {"unavailable": err}
+        for k in ("nccl_all_gather", "peer_stores"):
+            if "ms_per_step" in reassembly[k]:
+                reassembly[k]["nvlink_ingest_GBps_per_rank"] = \
+                    16.0 * (units_all - wl.units) / (reassembly[k]["ms_per_step"] * 1e-3) / 1e9
+        reassembly["nvlink_peak_GBps_per_direction"] = 770.0      # B200_PROFILING.md
+        if args.mode:
+            chosen = args.mode
+        else:
+            cands = {"nccl": reassembly["nccl_all_gather"]["ms_per_step"]}
+            if "ms_per_step" in reassembly["peer_stores"]:
+                cands["peer"] = reassembly["peer_stores"]["ms_per_step"]
+            chosen = min(cands, key=cands.get)
+        flag = torch.tensor([{"none": 0, "nccl": 1, "peer": 2}[chosen]], device="cuda")     # rank 0 decides
+        torch.distributed.broadcast(flag, src=0)
+        chosen = ("none", "nccl", "peer")[int(flag.item())]
+        reassembly["chosen"] = chosen
+        wl.set_mode(chosen)
+
+    total_ms, _, issue_us = timed_steps(wl.step, args.steps, args.warmup, world, sampler)
+    clocks = sampler.stop()
+    value = units_all * args.steps / (total_ms * 1e-3)
+    kernel_ms = kernel_time_ms(wl.step)
+    roofline = roofline_of(wl, kernel_ms)
+    # FK + query through the public API (set_joint_configuration is part of every control-loop iteration)
+    rq_ms, _, _ = timed_steps(wl.step_reconfigure, sub_steps, 3, world)
+    reconfigure = {"ms_per_step": rq_ms / sub_steps, "value": units_all * sub_steps / (rq_ms * 1e-3),
+                   "what": "RobotSDF.set_joint_configuration(q[200,7]) + the headline step, device-resident inputs"}
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_arm(wl, units_all, world, max(3, min(args.steps, 10)))
+        wl.restore()
+    cpu = None
+    if with_cpu:
+        with all_host_cpus(full_affinity):
+            cpu = cpu_baseline_of("c4")
+    launches = wl.launches_per_step * args.steps
+    wl.close()
+    desc = wl.desc
+    del wl
+    torch.cuda.empty_cache()
+
+    # ---- every other BASELINE config, same run ----
+    others = None
+    if args.workload == "default" and not args.no_workloads:
+        others = {}
+        for name in OTHER_WORKLOADS:
+            try:
+                w, res = run_workload(name, rank, world, min(args.steps, 30), args.warmup, not args.no_e2e,
+                                      with_cpu, None, full_affinity)
+                others[name] = res
+                del w
+            except Exception as e:      # a secondary workload never takes the headline down with it
+                others[name] = {"error": repr(e)[:300]}
+                if world > 1:
+                    raise               # ... but ranks must not diverge inside collectives
+            torch.cuda.empty_cache()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": desc,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "host_issue_us_per_step": issue_us, "cpu_baseline": cpu, "reassembly": reassembly,
+                "reconfigure_and_query": reconfigure,
+                "numa_binding": {"node": bound[0], "cpus": bound[1]} if bound else None,
+                "workloads": others}
+        print(json.dumps(line))
+    return finish(world)
+
+
+def finish(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
 
 
 if __name__ == "__main__":

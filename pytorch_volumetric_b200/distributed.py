@@ -27,6 +27,60 @@ def shard_range(n, rank, world):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index):
+    """NUMA node the GPU's PCIe root hangs off (sysfs), or None when the platform does not say."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+    except Exception:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()[-12:]
+        except Exception:
+            return None
+    try:
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read())
+        return node if node >= 0 else None
+    except (OSError, ValueError):
+        return None
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restrict this process to the CPUs of its GPU's NUMA node, so that the pinned host buffers it allocates from
+    now on (first touch) and the threads that fill them sit next to the PCIe root of that GPU.  With eight ranks
+    streaming results to host memory on a two-socket box, unbound ranks cross the socket interconnect and the
+    end-to-end time per step doubles (SCALE_r01: 3.7 ms at 1 GPU, 8.1 ms at 8).  Returns (node, n_cpus, previous
+    affinity) or None when nothing was changed; pass the previous affinity to os.sched_setaffinity to undo."""
+    import os
+    node = gpu_numa_node(device_index)
+    if node is None or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = _parse_cpulist(fh.read())
+        before = os.sched_getaffinity(0)
+        allowed = before & cpus
+        if not allowed or allowed == before:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node, len(allowed), before
+    except (OSError, ValueError):
+        return None
+
+
 def _world(group=None):
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
