@@ -40,8 +40,12 @@ def test_mesh_query_vs_oracle(name, n):
     bad_v, bad_g, rep = classify_mesh_mismatch(d_gpu[ok], g_gpu[ok], d_ref[ok], g_ref[ok], TOL, coord_scale=scale)
     assert bad_v == 0 and bad_g == 0, rep
     assert rep["bad_grad"] <= 5e-3 * n, rep
-    # closest point itself
-    assert np.abs(res.closest.cpu().numpy() - c_ref.numpy()).max() < 1e-5 or rep["explained"] > 0
+    # closest point itself: equal, or another point of the surface at the same distance (closest-feature tie)
+    c_gpu = res.closest.cpu().numpy()
+    moved = np.abs(c_gpu - c_ref.numpy()).max(-1) > 1e-5 * max(1.0, scale / 0.1)
+    d_own = np.linalg.norm(c_gpu.astype(np.float64) - pts.numpy(), axis=1)
+    assert (np.abs(d_own[moved] - np.abs(d_ref[moved])) < 5e-6 * max(1.0, scale / 0.1)).all()
+    assert moved.mean() < 5e-3
     # shapes / dtypes / device (sdf.py:166)
     assert res.distance.shape == (n,) and res.gradient.shape == (n, 3) and res.normal.shape == (n, 3)
     assert res.distance.dtype == torch.float32 and res.distance.device.type == "cuda"
