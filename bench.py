@@ -304,7 +304,7 @@ class C4(Workload):
     slabs (strong scaling); `mode` selects what a step leaves behind: "none" (every rank keeps its slab), "nccl"
     (all-gather of the slabs), "peer" (the kernel epilogue stores each slab into all ranks' buffers)."""
     name = "c4"
-    kernel = "composed_cfgmajor_kernel | composed_query_kernel<false,2,16> (by configuration-tile fill)"
+    kernel = "robot_query_kernel<8,unrolled> | composed_query_kernel<false,2,16> (by configuration-tile fill)"
 
     def __init__(self, rank, world=1, n_cfg=200, n_pts=100_000, cache_dir=None, mode="none"):
         import pytorch_volumetric_b200 as pv
@@ -411,6 +411,9 @@ class C5(Workload):
         begin, end = pd.shard_range(n_pts, rank, world)
         self.pts = world_pts[begin:end].contiguous()
         self.host_pts = self.pts.cpu().pin_memory()
+        # 60 MB cloud < L2: rotate 3 device copies (180 MB) so that no step finds its input in L2, instead of a flush
+        # memset inside the timed step
+        self.copies = [self.pts] + [self.pts.clone() for _ in range(2 if (end - begin) * 36 < 400e6 else 0)]
         pert = workloads.random_rigid(n_tf, seed=6, t_range=0.01).cuda()
         self.w2o = torch.linalg.inv(tf.unsqueeze(0)) @ pert
         self.units = (end - begin) * n_tf
@@ -421,12 +424,10 @@ class C5(Workload):
         self.pv = pv
         self.desc = {"workload": f"C5 chamfer: {n_pts}-point cloud -> 50 000-triangle bumpy sphere, B={n_tf} "
                                  f"transform(s), cloud sharded over ranks", "points_this_rank": end - begin,
-                     "l2_policy": "60 MB cloud fits L2: L2 flushed between steps by a 256 MB memset"}
-        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+                     "l2_policy": "60 MB cloud fits L2: 3 rotating device copies of the cloud (180 MB > L2)"}
 
     def step(self, i):
-        self.flush.zero_()
-        return self.pv.batch_chamfer_dist(self.w2o, self.pts, self.obj)
+        return self.pv.batch_chamfer_dist(self.w2o, self.copies[i % len(self.copies)], self.obj)
 
     def step_host(self, i):
         return self.pv.batch_chamfer_dist(self.w2o.cpu(), self.host_pts, self.obj)
@@ -455,6 +456,9 @@ class C3(Workload):
         b, e = pd.shard_range(len(pts), rank, world)
         self.host_pts = pts[b:e].contiguous().pin_memory()
         self.pts = self.host_pts.cuda()
+        # 24 MB of points + 32 MB of results per step fit L2: rotate 6 device copies of the point set (144 MB > L2)
+        # instead of a flush memset inside the timed step
+        self.copies = [self.pts] + [self.pts.clone() for _ in range(5)]
         self.units = e - b
         self.alg_bytes = 28 * self.units
         self.h2d_bytes = 12 * self.units
@@ -462,14 +466,12 @@ class C3(Workload):
         self.launches_per_step = 1
         self.desc = {"workload": f"C3 ComposedSDF of 16 drills ({'CachedSDF res=0.005' if cached else 'MeshSDF, one shared BVH'}) "
                                  f"random SE(3), 126^3 grid points + gradient", "points_this_rank": self.units,
-                     "l2_policy": "L2 flushed between steps by a 256 MB memset"}
-        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+                     "l2_policy": "6 rotating device copies of the point set (144 MB > L2); results are fresh buffers"}
         if cached:
             self.kernel = "composed_query_kernel<false>"
 
     def step(self, i):
-        self.flush.zero_()
-        return self.comp(self.pts)
+        return self.comp(self.copies[i % len(self.copies)])
 
     def step_host(self, i):
         return self.comp(self.host_pts)

@@ -205,6 +205,41 @@ int pvb_composed_query_multi(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
                              const float *pts, int64_t n_pts, uint32_t mesh_mode,
                              const pvb_out_target *targets, int32_t n_targets, int32_t *out_which, void *stream);
 
+/* ---- the same, stored through an NVLS MULTICAST mapping ----
+ * mc_val / mc_grad are multicast addresses (cuMulticast* / torch symmetric memory) of the full-size result buffers,
+ * already advanced to the slab: the kernel epilogue issues one multimem.st per 16-byte chunk and the NVSwitch
+ * replicates it into every bound GPU's buffer (the sender emits each byte once instead of once per peer).  Needs
+ * <= 16 GRID sub-SDFs with the bounding-box out-of-range rule (a RobotSDF of cached links). */
+int pvb_composed_query_multicast(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
+                                 int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count,
+                                 const float *pts, int64_t n_pts, uint32_t mesh_mode,
+                                 float *mc_val, float *mc_grad, void *stream);
+
+/* ---- RobotSDF.set_joint_configuration, model_to_sdf.py:82-115 (forward kinematics of a serial chain) ----
+ * For every configuration a and mesh link s: out[(slot_s * n_cfg + a)] = mesh_from_link_s @ inverse(FK_frame(s)(q_a)),
+ * the 4x4 row-major object->mesh-frame matrix pvb_composed_query reads (sub-SDF-major).  FK: T_f = T_{f-1} @ origin_f
+ * @ motion_f(q[q_index_f]); revolute = Rodrigues rotation about `axis` (unit), prismatic = translation along it.
+ * frames / links: HOST arrays (passed to the kernel by value); links sorted by frame; q DEVICE float[n_cfg][n_joints];
+ * out_xforms DEVICE float[n_links * n_cfg][16]. */
+#define PVB_FK_MAX_FRAMES 32
+#define PVB_FK_MAX_LINKS 16
+enum { PVB_FK_FIXED = 0, PVB_FK_REVOLUTE = 1, PVB_FK_PRISMATIC = 2 };
+typedef struct pvb_fk_frame {
+    float origin[12];      /* joint origin in the parent frame, rows of [R | t] */
+    float axis[3];
+    int32_t joint_type;    /* PVB_FK_* */
+    int32_t q_index;       /* column of q this joint reads (ignored for fixed joints) */
+    int32_t _pad[3];
+} pvb_fk_frame;
+typedef struct pvb_fk_link {
+    float mesh_from_link[12]; /* inverse of the visual offset (<visual><origin>), rows of [A | t] */
+    int32_t frame;            /* frame whose pose carries this mesh */
+    int32_t slot;             /* sub-SDF index s of the output */
+    int32_t _pad[2];
+} pvb_fk_link;
+int pvb_fk_serial(const pvb_fk_frame *frames, int32_t n_frames, const pvb_fk_link *links, int32_t n_links,
+                  const float *q, int32_t n_cfg, int32_t n_joints, float *out_xforms, void *stream);
+
 /* ---- peer-visible device buffers (one process per GPU, same node) ----
  * pvb_ipc_alloc: cudaMalloc on the current device (IPC handles need a whole allocation, not a slice of a caching
  * allocator's segment); pvb_ipc_export fills a 64-byte handle another PROCESS passes to pvb_ipc_open to map the

@@ -78,6 +78,22 @@ class SdfDesc(ctypes.Structure):
         return other
 
 
+class FkFrame(ctypes.Structure):
+    """Mirror of pvb_fk_frame (include/pvb.h)."""
+    _fields_ = [("origin", ctypes.c_float * 12), ("axis", ctypes.c_float * 3), ("joint_type", ctypes.c_int32),
+                ("q_index", ctypes.c_int32), ("_pad", ctypes.c_int32 * 3)]
+
+
+class FkLink(ctypes.Structure):
+    """Mirror of pvb_fk_link (include/pvb.h)."""
+    _fields_ = [("mesh_from_link", ctypes.c_float * 12), ("frame", ctypes.c_int32), ("slot", ctypes.c_int32),
+                ("_pad", ctypes.c_int32 * 2)]
+
+
+FK_FIXED, FK_REVOLUTE, FK_PRISMATIC = 0, 1, 2
+FK_MAX_FRAMES, FK_MAX_LINKS = 32, 16
+
+
 class OutTarget(ctypes.Structure):
     """Mirror of pvb_out_target (include/pvb.h)."""
     _fields_ = [("val", ctypes.c_void_p), ("grad", ctypes.c_void_p)]
@@ -117,6 +133,12 @@ _SIGNATURES = {
                                                 ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                 ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p,
                                                 ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    "pvb_composed_query_multicast": (ctypes.c_int, [ctypes.POINTER(SdfDesc), ctypes.c_int32, ctypes.c_int32,
+                                                    ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_void_p]),
+    "pvb_fk_serial": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
+                                     ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "pvb_ipc_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]),
     "pvb_ipc_free": (ctypes.c_int, [ctypes.c_void_p]),
     "pvb_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),

@@ -67,7 +67,7 @@ static int sm_count() {
 // Opt-in to > 48 KB of dynamic shared memory for `kernel`, once per (kernel, device).  `slot` is a small per-kernel
 // id; returns false when the runtime refuses.
 enum { kSlotMesh = 0, kSlotGridTma, kSlotCfgMajor, kSlotCfgMajorMulti, kSlotChamfer, kSlotRobot, kSlotRobotMulti,
-       kSlotRobotMc, kSlotCount };
+       kSlotRobotMc, kSlotRobotWide, kSlotRobotWideMulti, kSlotRobotWideMc, kSlotCount };
 template <typename K>
 static bool ensure_smem(K kernel, int slot, int bytes) {
     static unsigned char done[kSlotCount][kMaxDevices] = {{0}};
@@ -649,6 +649,7 @@ struct OutTargets {
     float *grad[PVB_MAX_TARGETS];
     int n;
     int vec;        // all pointers 16-byte aligned and n_pts % 4 == 0: rows may be stored as float4
+    int mc;         // val[0] / grad[0] are MULTICAST addresses (NVLS): one multimem.st reaches every bound GPU
 };
 
 template <bool kMesh, int PTS, int MAXS, bool kMulti>
@@ -925,6 +926,373 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
             }
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// RobotSDF kernel, second generation (round 2): the configuration-major scheme above, specialised to what a
+// RobotSDF with cached links is -- every sub-SDF a GRID with the bounding-box out-of-range rule -- and rebuilt around
+// what the round-1 profile of composed_cfgmajor_kernel showed (profiles/r02/): 29 warp-instructions per
+// (configuration, point) pair, 142 LDC + 183 MOV in the SASS because the descriptors were indexed with a run-time
+// link number, 80 registers (3 CTAs per SM, 36 % warps active), four scalar stores per pair.
+//   * the host passes the descriptors ALREADY in visiting order and the link loop is fully unrolled, so every
+//     descriptor field is a constant-bank operand of the instruction that uses it (no LDC, no MOV, no index math);
+//   * the transforms and bounding spheres are staged in visiting order as well: shared-memory addresses are
+//     lane base + immediate;
+//   * results leave through a row-major staging tile ([cfg][32 values], [cfg][96 gradient floats]) written with
+//     conflict-free STS.128 and read back as whole 512-byte rows: ONE 16-byte store per lane and destination (lanes
+//     0-7 the values, lanes 8-31 the gradients), for the local buffer, for peer buffers (kDest 1) and for a
+//     multicast mapping (kDest 2: one multimem.st reaches every GPU of the NVSwitch domain);
+//   * the four points of a thread are one 48-byte uniform vector load.
+// Arithmetic is composed_xform / composed_aabb_lb2 / grid_eval / composed_rotate_back exactly as in the other two
+// composed kernels, so results are bit-identical to them (tests/test_gpu_composed.py).
+#ifndef PVB_ROBOT_PTS
+#define PVB_ROBOT_PTS 4       // points per thread (4 or 2)
+#endif
+#ifndef PVB_ROBOT_MINB
+#define PVB_ROBOT_MINB 4      // resident CTAs per SM the unrolled instantiation is compiled for (register budget)
+#endif
+constexpr int kRbCfg = 32;                        // lanes = configurations
+constexpr int kRbWarps = 8;
+constexpr int kRbPts = PVB_ROBOT_PTS;             // points per thread
+static_assert(kRbPts == 4 || kRbPts == 2, "PVB_ROBOT_PTS must be 2 or 4");
+constexpr int kRbTilePts = kRbWarps * kRbPts;     // 32 (16): one output row of a tile
+constexpr int kRbValStride = kRbTilePts + 4;      // floats; rows stay 16-byte aligned, vector STS conflict-free
+constexpr int kRbGradStride = 3 * kRbTilePts + 4; // floats
+
+template <int MAXS>
+struct RobotPack {
+    pvb_sdf_desc d[MAXS];       // visiting order
+    int orig[MAXS];             // visiting position -> original sub-SDF index (transforms, tie rule, out_which)
+};
+
+template <int MAXS>
+struct __align__(16) RobotSmem {
+    float4 xf[kRbCfg][3 * MAXS + 1];              // row stride = odd number of float4: conflict-free LDS.128
+    float4 sph[kRbCfg][MAXS + 1];
+    float outv[kRbCfg][kRbValStride];
+    float outg[kRbCfg][kRbGradStride];
+};
+
+__device__ __forceinline__ void st_mc_v4(float *mc, float4 v) {     // one store, every GPU of the multicast group
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_mc_f32(float *mc, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+
+// Everything that is not "in range, fp32 index estimate certain" -- the exact index of a point inside a cell
+// boundary's uncertainty band, or the point-to-AABB rule of an out-of-range point -- out of line and through a
+// pointer to the descriptor in parameter space: rare, and 32 inlined copies of it (4 points x 8 unrolled links) were
+// two thirds of the kernel's code.
+__device__ __noinline__ float4 robot_lookup_slow(const pvb_sdf_desc *dp, float qx, float qy, float qz) {
+    const pvb_sdf_desc &d = *dp;
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    const SdfOut o = grid_eval<false, true>(d, st, mk3(qx, qy, qz), 0u, 0ull, nullptr);
+    return make_float4(o.val, o.grad.x, o.grad.y, o.grad.z);
+}
+
+// In-range + certain: the record of the nearest voxel, same arithmetic as grid_eval (pvb_device.cuh).
+__device__ __forceinline__ float4 robot_lookup(const pvb_sdf_desc &g, f3 p) {
+    const float kMagic = 12582912.f;   // 1.5 * 2^23
+    const float qx = (p.x - g.min32[0]) * g.inv_res32[0];
+    const float qy = (p.y - g.min32[1]) * g.inv_res32[1];
+    const float qz = (p.z - g.min32[2]) * g.inv_res32[2];
+    const float mx = __fadd_rn(qx, kMagic), my = __fadd_rn(qy, kMagic), mz = __fadd_rn(qz, kMagic);
+    const int kx = __float_as_int(mx) - 0x4B400000, ky = __float_as_int(my) - 0x4B400000,
+              kz = __float_as_int(mz) - 0x4B400000;
+    const bool certain = (fabsf(qx - __fsub_rn(mx, kMagic)) <= g.idx_certain[0]) &
+                         (fabsf(qy - __fsub_rn(my, kMagic)) <= g.idx_certain[1]) &
+                         (fabsf(qz - __fsub_rn(mz, kMagic)) <= g.idx_certain[2]);
+    const bool inb = (p.x >= g.valid_lo[0]) & (p.x <= g.valid_hi[0]) & (p.y >= g.valid_lo[1]) &
+                     (p.y <= g.valid_hi[1]) & (p.z >= g.valid_lo[2]) & (p.z <= g.valid_hi[2]);
+    if (inb & certain)      // the index is exact and inside the table: no clamp needed
+        return __ldg(reinterpret_cast<const float4 *>(g.table) + ((kx * g.dims[1] + ky) * g.dims[2] + kz));
+    return robot_lookup_slow(&g, p.x, p.y, p.z);
+}
+
+// kDest: 0 = out_val / out_grad, 1 = every (val, grad) pair of tg, 2 = tg.val[0] / tg.grad[0] are multicast addresses
+template <int MAXS, bool kUnroll, int kDest>
+__global__ void __launch_bounds__(kRbCfg * kRbWarps, kUnroll ? PVB_ROBOT_MINB : 3)
+robot_query_kernel(const __grid_constant__ RobotPack<MAXS> pk, int n_sdf, const float *__restrict__ xforms, int n_cfg,
+                   int cfg_begin, int cfg_count, const float *__restrict__ pts, int n_pts, int vec,
+                   float *__restrict__ out_val, float *__restrict__ out_grad, int *__restrict__ out_which,
+                   const __grid_constant__ OutTargets tg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RobotSmem<MAXS> &sm = *reinterpret_cast<RobotSmem<MAXS> *>(smem_raw);
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.y * kRbCfg;                       // first configuration (relative to cfg_begin)
+    const int ncfg = min(kRbCfg, cfg_count - c0);
+    // ---- stage transforms + object-frame bounding spheres of this configuration tile, in visiting order ----
+    for (int item = threadIdx.x; item < kRbCfg * n_sdf; item += blockDim.x) {
+        const int ci = item % kRbCfg, si = item / kRbCfg;
+        const pvb_sdf_desc &d = pk.d[si];
+        float4 r0 = make_float4(1.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 1.f, 0.f, 0.f),
+               r2 = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (ci < ncfg) {
+            const float4 *row =
+                reinterpret_cast<const float4 *>(xforms + ((size_t)pk.orig[si] * n_cfg + cfg_begin + c0 + ci) * 16);
+            r0 = __ldg(row); r1 = __ldg(row + 1); r2 = __ldg(row + 2);
+        }
+        sm.xf[ci][3 * si] = r0; sm.xf[ci][3 * si + 1] = r1; sm.xf[ci][3 * si + 2] = r2;
+        // sphere around the link AABB, centre carried to the object frame: c_obj = R^T (c_link - t)
+        const f3 cl = mk3(0.5f * (d.bb_min[0] + d.bb_max[0]), 0.5f * (d.bb_min[1] + d.bb_max[1]),
+                          0.5f * (d.bb_min[2] + d.bb_max[2]));
+        const f3 hl = mk3(0.5f * (d.bb_max[0] - d.bb_min[0]), 0.5f * (d.bb_max[1] - d.bb_min[1]),
+                          0.5f * (d.bb_max[2] - d.bb_min[2]));
+        const f3 u = mk3(cl.x - r0.w, cl.y - r1.w, cl.z - r2.w);
+        const f3 co = mk3(r0.x * u.x + r1.x * u.y + r2.x * u.z, r0.y * u.x + r1.y * u.y + r2.y * u.z,
+                          r0.z * u.x + r1.z * u.y + r2.z * u.z);
+        float rad = sqrtf(hl.x * hl.x + hl.y * hl.y + hl.z * hl.z) * 1.0001f + 1e-6f;
+        // the bound needs an isometry: |R R^T - I| must vanish, otherwise this (cfg, link) never prunes in stage 1
+        const float e00 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z - 1.f, e11 = r1.x * r1.x + r1.y * r1.y + r1.z * r1.z - 1.f,
+                    e22 = r2.x * r2.x + r2.y * r2.y + r2.z * r2.z - 1.f;
+        const float e01 = r0.x * r1.x + r0.y * r1.y + r0.z * r1.z, e02 = r0.x * r2.x + r0.y * r2.y + r0.z * r2.z,
+                    e12 = r1.x * r2.x + r1.y * r2.y + r1.z * r2.z;
+        const float dev = fmaxf(fmaxf(fmaxf(fabsf(e00), fabsf(e11)), fmaxf(fabsf(e22), fabsf(e01))),
+                                fmaxf(fabsf(e02), fabsf(e12)));
+        const bool ok = (d.flags & PVB_GRID_PRUNE_OK) && dev < 1e-5f;
+        rad = ok ? rad + d.prune_margin : PVB_INF;
+        sm.sph[ci][si] = make_float4(co.x, co.y, co.z, rad);
+    }
+    __syncthreads();
+    const bool lane_on = lane < ncfg;
+    const int n_tiles = (n_pts + kRbTilePts - 1) / kRbTilePts;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int pt0 = tile * kRbTilePts + warp * kRbPts;
+        const bool full_tile = tile * kRbTilePts + kRbTilePts <= n_pts;
+        f3 p[kRbPts];
+        // validity of the thread's points as a bit mask (bit k = point pt0 + k exists and this lane has a configuration)
+        unsigned on_mask;
+        if (vec && full_tile) {           // the thread's points are contiguous and the same for every lane: uniform vector loads
+            if constexpr (kRbPts == 4) {
+                const float4 *src = reinterpret_cast<const float4 *>(pts + 3 * (size_t)pt0);
+                const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+                p[0] = mk3(a.x, a.y, a.z); p[1] = mk3(a.w, b.x, b.y); p[2] = mk3(b.z, b.w, c.x); p[3] = mk3(c.y, c.z, c.w);
+            } else {
+                const float2 *src = reinterpret_cast<const float2 *>(pts + 3 * (size_t)pt0);
+                const float2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+                p[0] = mk3(a.x, a.y, b.x); p[1] = mk3(b.y, c.x, c.y);
+            }
+            on_mask = lane_on ? ((1u << kRbPts) - 1u) : 0u;
+        } else {
+            on_mask = 0u;
+#pragma unroll
+            for (int k = 0; k < kRbPts; ++k) {
+                const bool in = pt0 + k < n_pts;
+                if (lane_on && in) on_mask |= 1u << k;
+                p[k] = in ? load_point(pts, pt0 + k) : mk3(0.f, 0.f, 0.f);
+            }
+        }
+        float best[kRbPts];
+        f3 bg[kRbPts];
+        int bs[kRbPts];
+#pragma unroll
+        for (int k = 0; k < kRbPts; ++k) { best[k] = PVB_INF; bg[k] = mk3(0.f, 0.f, 0.f); bs[k] = -1; }
+
+        // One link: stage 1 (object-frame bounding sphere against the running minimum, no transform), then for the
+        // points that survive: transform, AABB bound, nearest-voxel lookup, running argmin (first index on ties).
+        auto link = [&](const int si) {
+            const pvb_sdf_desc &d = pk.d[si];
+            const int s = pk.orig[si];
+            const float4 sp = sm.sph[lane][si];
+            unsigned need = 0u;
+#pragma unroll
+            for (int k = 0; k < kRbPts; ++k) {
+                // value >= |p - c_obj| - radius - margin (isometry); 0.9998 absorbs the 1e-5 non-rigidity
+                const float thr = best[k] + sp.w;
+                const float dx = p[k].x - sp.x, dy = p[k].y - sp.y, dz = p[k].z - sp.z;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                const bool pruned = bs[k] >= 0 && (thr < 0.f || d2 * 0.9998f > thr * thr);
+                if (!pruned) need |= 1u << k;
+            }
+            need &= on_mask;
+            if (need == 0u) return;
+            const float4 r0 = sm.xf[lane][3 * si], r1 = sm.xf[lane][3 * si + 1], r2 = sm.xf[lane][3 * si + 2];
+#pragma unroll
+            for (int k = 0; k < kRbPts; ++k) {
+                if (!(need & (1u << k))) continue;
+                const f3 q = composed_xform(r0, r1, r2, p[k]);
+                if ((d.flags & PVB_GRID_PRUNE_OK) && bs[k] >= 0) {
+                    const float thr = best[k] + d.prune_margin;
+                    if (thr < 0.f || composed_aabb_lb2(d, q) > thr * thr) continue;
+                }
+                const float4 o = robot_lookup(d, q);
+                if (bs[k] < 0 || o.x < best[k] || (o.x == best[k] && s < bs[k])) {
+                    best[k] = o.x; bg[k] = mk3(o.y, o.z, o.w); bs[k] = s;
+                }
+            }
+        };
+        if constexpr (kUnroll) {
+#pragma unroll
+            for (int si = 0; si < MAXS; ++si) {
+                if (si < n_sdf) link(si);
+            }
+        } else {
+#pragma unroll 1
+            for (int si = 0; si < n_sdf; ++si) link(si);
+        }
+        // ---- winning gradients back to the object frame (g @ M[:3,:3]); park the thread's 4 values + 12 gradient
+        // floats as 4 x STS.128 into the row-major staging tile ----
+        float gout[3 * kRbPts];
+#pragma unroll
+        for (int k = 0; k < kRbPts; ++k) {
+            // visiting position of the winner: the transforms are staged in visiting order
+            int sb = 0;
+#pragma unroll
+            for (int si = 0; si < MAXS; ++si)
+                if (si < n_sdf && pk.orig[si] == bs[k]) sb = si;
+            const f3 go = composed_rotate_back(sm.xf[lane][3 * sb], sm.xf[lane][3 * sb + 1], sm.xf[lane][3 * sb + 2], bg[k]);
+            gout[3 * k] = go.x; gout[3 * k + 1] = go.y; gout[3 * k + 2] = go.z;
+        }
+        if constexpr (kRbPts == 4) {
+            *reinterpret_cast<float4 *>(&sm.outv[lane][warp * kRbPts]) = make_float4(best[0], best[1], best[2], best[3]);
+            float4 *dg = reinterpret_cast<float4 *>(&sm.outg[lane][3 * warp * kRbPts]);
+            dg[0] = make_float4(gout[0], gout[1], gout[2], gout[3]);
+            dg[1] = make_float4(gout[4], gout[5], gout[6], gout[7]);
+            dg[2] = make_float4(gout[8], gout[9], gout[10], gout[11]);
+        } else {
+            *reinterpret_cast<float2 *>(&sm.outv[lane][warp * kRbPts]) = make_float2(best[0], best[1]);
+            float2 *dg = reinterpret_cast<float2 *>(&sm.outg[lane][3 * warp * kRbPts]);
+            dg[0] = make_float2(gout[0], gout[1]);
+            dg[1] = make_float2(gout[2], gout[3]);
+            dg[2] = make_float2(gout[4], gout[5]);
+        }
+        if (out_which) {            // diagnostic output (tests): strided, not on the fast path
+#pragma unroll
+            for (int k = 0; k < kRbPts; ++k)
+                if (on_mask & (1u << k)) out_which[(size_t)(c0 + lane) * n_pts + pt0 + k] = bs[k];
+        }
+        __syncthreads();
+        if (vec && full_tile) {
+            // one configuration row of the tile = kRbTilePts values + 3 * kRbTilePts gradient floats, both contiguous
+            // in the output = kRbTilePts 16-byte chunks (the first quarter values, the rest gradients): one 16-byte
+            // store per lane and destination, whole sectors; 32 / kRbTilePts rows per warp instruction
+            constexpr int kRowsPerInstr = 32 / kRbTilePts;
+            const int chunk = lane % kRbTilePts;
+            const bool is_val = chunk < kRbTilePts / 4;
+            for (int r = warp * kRowsPerInstr + lane / kRbTilePts; r < ncfg; r += kRbWarps * kRowsPerInstr) {
+                const float4 v4 = is_val ? *reinterpret_cast<const float4 *>(&sm.outv[r][4 * chunk])
+                                         : *reinterpret_cast<const float4 *>(&sm.outg[r][4 * (chunk - kRbTilePts / 4)]);
+                const size_t o_row = (size_t)(c0 + r) * n_pts + (size_t)tile * kRbTilePts;
+                const size_t off = is_val ? o_row + 4 * chunk : 3 * o_row + 4 * (chunk - kRbTilePts / 4);
+                if constexpr (kDest == 0) {
+                    __stcs(reinterpret_cast<float4 *>((is_val ? out_val : out_grad) + off), v4);
+                } else if constexpr (kDest == 1) {
+                    for (int t = 0; t < tg.n; ++t)
+                        __stcs(reinterpret_cast<float4 *>((is_val ? tg.val[t] : tg.grad[t]) + off), v4);
+                } else {
+                    st_mc_v4((is_val ? tg.val[0] : tg.grad[0]) + off, v4);
+                }
+            }
+        } else {
+            const int pt = tile * kRbTilePts + lane;
+            if (pt < n_pts) {
+                for (int r = warp; r < ncfg; r += kRbWarps) {
+                    const float v = sm.outv[r][lane];
+                    const float gx = sm.outg[r][3 * lane], gy = sm.outg[r][3 * lane + 1], gz = sm.outg[r][3 * lane + 2];
+                    const size_t o_i = (size_t)(c0 + r) * n_pts + pt;
+                    if constexpr (kDest == 0) {
+                        __stcs(out_val + o_i, v);
+                        __stcs(out_grad + 3 * o_i, gx); __stcs(out_grad + 3 * o_i + 1, gy); __stcs(out_grad + 3 * o_i + 2, gz);
+                    } else if constexpr (kDest == 1) {
+                        for (int t = 0; t < tg.n; ++t) {
+                            __stcs(tg.val[t] + o_i, v);
+                            __stcs(tg.grad[t] + 3 * o_i, gx); __stcs(tg.grad[t] + 3 * o_i + 1, gy);
+                            __stcs(tg.grad[t] + 3 * o_i + 2, gz);
+                        }
+                    } else {
+                        st_mc_f32(tg.val[0] + o_i, v);
+                        st_mc_f32(tg.grad[0] + 3 * o_i, gx); st_mc_f32(tg.grad[0] + 3 * o_i + 1, gy);
+                        st_mc_f32(tg.grad[0] + 3 * o_i + 2, gz);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ======================================================== forward kinematics
+// RobotSDF.set_joint_configuration (model_to_sdf.py:82-115): for every joint configuration a and every mesh link s,
+// the object->mesh-frame transform (FK_s(q_a) @ visual_offset_s)^-1 = offset_s^-1 @ FK_s(q_a)^-1, written link-major
+// (row s * A + a) as the 4x4 row-major matrices the composed kernels read.  One thread per configuration walks the
+// serial chain in registers: T <- T @ joint_origin @ motion(q_j) (revolute: Rodrigues rotation about the axis,
+// prismatic: translation along it, fixed: identity), the same fp32 products the eager path took as dozens of small
+// launches (2.4 ms for 200 configurations of a 7-joint arm; this kernel: microseconds).
+struct FkPlan {
+    pvb_fk_frame frame[PVB_FK_MAX_FRAMES];
+    pvb_fk_link link[PVB_FK_MAX_LINKS];
+    int n_frames, n_links;
+};
+
+struct Rt34 { float m[12]; };       // rows of [R | t]
+
+__device__ __forceinline__ Rt34 rt_mul(const Rt34 &a, const float *b) {       // a @ b, both [R | t] with last row 0 0 0 1
+    Rt34 o;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v = a.m[4 * r] * b[c] + a.m[4 * r + 1] * b[4 + c] + a.m[4 * r + 2] * b[8 + c];
+            if (c == 3) v += a.m[4 * r + 3];
+            o.m[4 * r + c] = v;
+        }
+    }
+    return o;
+}
+
+__global__ void fk_serial_kernel(const __grid_constant__ FkPlan plan, const float *__restrict__ q, int n_cfg,
+                                 int n_joints, float *__restrict__ out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_cfg) return;
+    Rt34 cur;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) cur.m[e] = (e % 5 == 0) ? 1.f : 0.f;
+    int next_link = 0;
+    for (int f = 0; f < plan.n_frames; ++f) {
+        const pvb_fk_frame &fr = plan.frame[f];
+        cur = rt_mul(cur, fr.origin);
+        if (fr.joint_type != PVB_FK_FIXED) {
+            const float th = __ldg(q + (size_t)a * n_joints + fr.q_index);
+            float mot[12];
+            const float x = fr.axis[0], y = fr.axis[1], z = fr.axis[2];
+            if (fr.joint_type == PVB_FK_REVOLUTE) {
+                const float c = cosf(th), s = sinf(th), t = 1.f - c;
+                mot[0] = c + x * x * t;     mot[1] = x * y * t - z * s; mot[2] = x * z * t + y * s;  mot[3] = 0.f;
+                mot[4] = y * x * t + z * s; mot[5] = c + y * y * t;     mot[6] = y * z * t - x * s;  mot[7] = 0.f;
+                mot[8] = z * x * t - y * s; mot[9] = z * y * t + x * s; mot[10] = c + z * z * t;     mot[11] = 0.f;
+            } else {
+                mot[0] = 1.f; mot[1] = 0.f; mot[2] = 0.f; mot[3] = x * th;
+                mot[4] = 0.f; mot[5] = 1.f; mot[6] = 0.f; mot[7] = y * th;
+                mot[8] = 0.f; mot[9] = 0.f; mot[10] = 1.f; mot[11] = z * th;
+            }
+            cur = rt_mul(cur, mot);
+        }
+        // mesh links attached to this frame (sorted by frame on the host)
+        while (next_link < plan.n_links && plan.link[next_link].frame == f) {
+            const pvb_fk_link &lk = plan.link[next_link];
+            // rigid inverse of the link pose: [R^T | -R^T t]
+            float inv[12];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                inv[4 * r] = cur.m[r]; inv[4 * r + 1] = cur.m[4 + r]; inv[4 * r + 2] = cur.m[8 + r];
+                inv[4 * r + 3] = -(cur.m[r] * cur.m[3] + cur.m[4 + r] * cur.m[7] + cur.m[8 + r] * cur.m[11]);
+            }
+            Rt34 off;
+#pragma unroll
+            for (int e = 0; e < 12; ++e) off.m[e] = lk.mesh_from_link[e];
+            const Rt34 m = rt_mul(off, inv);
+            float4 *dst = reinterpret_cast<float4 *>(out + ((size_t)lk.slot * n_cfg + a) * 16);
+            dst[0] = make_float4(m.m[0], m.m[1], m.m[2], m.m[3]);
+            dst[1] = make_float4(m.m[4], m.m[5], m.m[6], m.m[7]);
+            dst[2] = make_float4(m.m[8], m.m[9], m.m[10], m.m[11]);
+            dst[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+            ++next_link;
+        }
     }
 }
 
@@ -1312,6 +1680,53 @@ static int launch_composed(const pvb_sdf_desc *descs, int n_sdf, const float *xf
     return PVB_OK;
 }
 
+// Launch robot_query_kernel (all sub-SDFs GRID with the bounding-box rule, <= 16 of them).
+template <int MAXS, bool kUnroll>
+static int launch_robot(const pvb_sdf_desc *descs, int n_sdf, const float *xforms, int n_cfg, int cfg_begin,
+                        int cfg_count, const float *pts, long long n_pts, int vec, float *out_val, float *out_grad,
+                        int *out_which, const OutTargets *tg, cudaStream_t stream) {
+    RobotPack<MAXS> pack;
+    memset(&pack, 0, sizeof(pack));
+    DescPack<MAXS> order;               // only its visiting order is used
+    fill_order(order, n_sdf);
+    for (int si = 0; si < n_sdf; ++si) {
+        pack.d[si] = descs[order.order[si]];
+        pack.orig[si] = order.order[si];
+    }
+    for (int si = n_sdf; si < MAXS; ++si) pack.orig[si] = -1;
+    const int kind = !tg ? 0 : (tg->mc ? 2 : 1);
+    auto k0 = robot_query_kernel<MAXS, kUnroll, 0>;
+    auto k1 = robot_query_kernel<MAXS, kUnroll, 1>;
+    auto k2 = robot_query_kernel<MAXS, kUnroll, 2>;
+    const int smem = (int)sizeof(RobotSmem<MAXS>);
+    const int slot0 = kUnroll ? kSlotRobot : kSlotRobotWide;
+    if (!ensure_smem(k0, slot0, smem) || !ensure_smem(k1, slot0 + 1, smem) || !ensure_smem(k2, slot0 + 2, smem)) {
+        pvb_set_error("pvb_composed_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+        return PVB_ERR_CUDA;
+    }
+    const int gy = (cfg_count + kRbCfg - 1) / kRbCfg;
+    const long long n_tiles = (n_pts + kRbTilePts - 1) / kRbTilePts;
+    static const int waves = [] { const char *e = getenv("PVB_ROBOT_WAVES"); return e ? atoi(e) : 4; }();
+    long long gx = ((long long)sm_count() * (kUnroll ? 4 : 3) * waves + gy - 1) / gy;
+    if (gx > n_tiles) gx = n_tiles;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    const OutTargets none{};
+    timing_mark(0, stream);
+    if (kind == 0)
+        k0<<<grid, kRbCfg * kRbWarps, smem, stream>>>(pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, (int)n_pts,
+                                                      vec, out_val, out_grad, out_which, none);
+    else if (kind == 1)
+        k1<<<grid, kRbCfg * kRbWarps, smem, stream>>>(pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, (int)n_pts,
+                                                      vec, nullptr, nullptr, out_which, *tg);
+    else
+        k2<<<grid, kRbCfg * kRbWarps, smem, stream>>>(pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, (int)n_pts,
+                                                      vec, nullptr, nullptr, out_which, *tg);
+    timing_mark(1, stream);
+    PVB_CHECK_LAUNCH("pvb_composed_query(robot)");
+    return PVB_OK;
+}
+
 // tg == nullptr: one destination (out_val / out_grad); otherwise the kMulti instantiations store to every target
 static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
                              int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count, const float *pts, int64_t n_pts,
@@ -1339,6 +1754,16 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
         tgv.vec = out_aligned && (n_pts % 4 == 0);
         tg = &tgv;
     }
+    if (tg && tg->mc) {
+        // multicast destinations exist only in robot_query_kernel: refuse anything that would fall through
+        bool grids = !needs_mesh && n_sdf <= 16;
+        for (int i = 0; i < n_sdf && grids; ++i)
+            grids = descs[i].kind == PVB_KIND_GRID && !(descs[i].flags & (PVB_GRID_OOB_GT | PVB_GRID_TRILINEAR));
+        if (!grids || n_pts >= (1ll << 31)) {
+            pvb_set_error("pvb_composed_query_multicast: needs <= 16 GRID sub-SDFs with the bounding-box rule");
+            return PVB_ERR_INVALID;
+        }
+    }
     const bool vec = !needs_mesh && aligned16(pts) && out_aligned && aligned16(out_which) && (n_pts % 4 == 0);
     const long long n_vec = vec ? n_pts : 0;
     int rc = PVB_OK;
@@ -1350,6 +1775,20 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
     // sectors, which is what the NVLink-bound re-assembly needs; idle lanes cost less than partial-sector packets
     const bool cm_filled = (cfg_count >= 16 && (double)cfg_count >= 0.85 * (double)(cm_tiles * kCmCfg)) ||
                            (tg && tg->vec && cfg_count >= 8);
+    static const int robot_kernel = [] { const char *e = getenv("PVB_ROBOT_KERNEL"); return e ? atoi(e) : 1; }();
+    static const double robot_fill = [] { const char *e = getenv("PVB_ROBOT_MIN_FILL"); return e ? atof(e) : 0.85; }();
+    bool all_grid = !needs_mesh && n_sdf <= 16 && n_pts < (1ll << 31);
+    for (int i = 0; i < n_sdf && all_grid; ++i)
+        all_grid = descs[i].kind == PVB_KIND_GRID && !(descs[i].flags & (PVB_GRID_OOB_GT | PVB_GRID_TRILINEAR));
+    const bool rb_filled = (cfg_count >= 16 && (double)cfg_count >= robot_fill * (double)(cm_tiles * kCmCfg)) ||
+                           (tg && tg->vec && cfg_count >= 8) || (tg && tg->mc);
+    if (robot_kernel && cfg_major && all_grid && rb_filled) {
+        const int vec_rows = (tg ? tg->vec : (out_aligned && (n_pts % 4 == 0))) && aligned16(pts);
+        return n_sdf <= 8 ? launch_robot<8, true>(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, vec_rows,
+                                                  out_val, out_grad, out_which, tg, s)
+                          : launch_robot<16, false>(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts,
+                                                    vec_rows, out_val, out_grad, out_which, tg, s);
+    }
     if (cfg_major && !needs_mesh && n_sdf <= kCmMaxS && cm_filled) {
         if (!ensure_smem(composed_cfgmajor_kernel<false>, kSlotCfgMajor, (int)sizeof(CmSmem)) ||
             !ensure_smem(composed_cfgmajor_kernel<true>, kSlotCfgMajorMulti, (int)sizeof(CmSmem))) {
@@ -1424,6 +1863,23 @@ extern "C" int pvb_composed_query_multi(const pvb_sdf_desc *descs, int32_t n_sdf
                              tg.val[0], tg.grad[0], out_which, &tg, stream);
 }
 
+extern "C" int pvb_composed_query_multicast(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh,
+                                            const float *xforms, int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count,
+                                            const float *pts, int64_t n_pts, uint32_t mesh_mode, float *mc_val,
+                                            float *mc_grad, void *stream) {
+    if (!mc_val || !mc_grad || ((uintptr_t)mc_val % 16) || ((uintptr_t)mc_grad % 16)) {
+        pvb_set_error("pvb_composed_query_multicast: multicast addresses must be non-null and 16-byte aligned");
+        return PVB_ERR_INVALID;
+    }
+    OutTargets tg{};
+    tg.n = 1;
+    tg.mc = 1;
+    tg.val[0] = mc_val;
+    tg.grad[0] = mc_grad;
+    return composed_dispatch(descs, n_sdf, needs_mesh, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, mesh_mode,
+                             mc_val, mc_grad, nullptr, &tg, stream);
+}
+
 // ------------------------------------------------------------------------------------------------ peer buffers
 #define PVB_CUDA_TRY(call, what)                                                                     \
     do {                                                                                             \
@@ -1466,6 +1922,46 @@ extern "C" int pvb_ipc_open(const unsigned char *handle, void **out_ptr) {
 extern "C" int pvb_ipc_close(void *ptr) {
     if (!ptr) return PVB_OK;
     PVB_CUDA_TRY(cudaIpcCloseMemHandle(ptr), "pvb_ipc_close(cudaIpcCloseMemHandle)");
+    return PVB_OK;
+}
+
+extern "C" int pvb_fk_serial(const pvb_fk_frame *frames, int32_t n_frames, const pvb_fk_link *links, int32_t n_links,
+                             const float *q, int32_t n_cfg, int32_t n_joints, float *out_xforms, void *stream) {
+    if (!frames || !links || n_frames < 1 || n_frames > PVB_FK_MAX_FRAMES || n_links < 1 || n_links > PVB_FK_MAX_LINKS ||
+        n_cfg < 0 || n_joints < 0 || (n_cfg > 0 && (!out_xforms || (n_joints > 0 && !q)))) {
+        pvb_set_error("pvb_fk_serial: invalid argument (n_frames=%d n_links=%d n_cfg=%d n_joints=%d)", n_frames, n_links,
+                      n_cfg, n_joints);
+        return PVB_ERR_INVALID;
+    }
+    if ((uintptr_t)out_xforms % 16) {
+        pvb_set_error("pvb_fk_serial: out_xforms must be 16-byte aligned");
+        return PVB_ERR_INVALID;
+    }
+    FkPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    plan.n_frames = n_frames;
+    plan.n_links = n_links;
+    memcpy(plan.frame, frames, sizeof(pvb_fk_frame) * (size_t)n_frames);
+    memcpy(plan.link, links, sizeof(pvb_fk_link) * (size_t)n_links);
+    int prev = -1;
+    for (int s = 0; s < n_links; ++s) {
+        const pvb_fk_link &lk = plan.link[s];
+        if (lk.frame < prev || lk.frame < 0 || lk.frame >= n_frames || lk.slot < 0 || lk.slot >= n_links) {
+            pvb_set_error("pvb_fk_serial: links must be sorted by frame, with frame in [0, n_frames) and slot in [0, n_links)");
+            return PVB_ERR_INVALID;
+        }
+        prev = lk.frame;
+    }
+    for (int f = 0; f < n_frames; ++f) {
+        const pvb_fk_frame &fr = plan.frame[f];
+        if (fr.joint_type != PVB_FK_FIXED && (fr.q_index < 0 || fr.q_index >= n_joints)) {
+            pvb_set_error("pvb_fk_serial: frame %d reads joint value %d of %d", f, fr.q_index, n_joints);
+            return PVB_ERR_INVALID;
+        }
+    }
+    if (n_cfg == 0) return PVB_OK;
+    fk_serial_kernel<<<(n_cfg + 63) / 64, 64, 0, (cudaStream_t)stream>>>(plan, q, n_cfg, n_joints, out_xforms);
+    PVB_CHECK_LAUNCH("pvb_fk_serial");
     return PVB_OK;
 }
 

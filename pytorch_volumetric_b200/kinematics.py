@@ -114,6 +114,29 @@ class SerialChain:
                 return f
         return None
 
+    def native_fk_frames(self):
+        """The chain as the pvb_fk_frame array pvb_fk_serial takes (include/pvb.h): joint origins, unit axes, joint
+        types and the column of q each movable joint reads.  fp32, like forward_kinematics on a float32 chain."""
+        from . import _native as nat
+        if len(self._frames) > nat.FK_MAX_FRAMES:
+            return None
+        arr = (nat.FkFrame * len(self._frames))()
+        j = 0
+        for i, f in enumerate(self._frames):
+            o = f.joint.origin.to(torch.float32)
+            for r in range(3):
+                for c in range(4):
+                    arr[i].origin[4 * r + c] = float(o[r, c])
+            ax = f.joint.axis.to(torch.float32)
+            for k in range(3):
+                arr[i].axis[k] = float(ax[k])
+            jt = f.joint.joint_type
+            arr[i].joint_type = {"revolute": nat.FK_REVOLUTE, "prismatic": nat.FK_PRISMATIC}.get(jt, nat.FK_FIXED)
+            arr[i].q_index = j if jt != "fixed" else -1
+            if jt != "fixed":
+                j += 1
+        return arr
+
     def forward_kinematics(self, th, end_only=True):
         th = torch.as_tensor(th, dtype=self.dtype, device=self.device)
         if th.dim() == 1:

@@ -65,7 +65,36 @@ class RobotSDF(sdf.ObjectFrameSDF):
         # inverse of the visual offsets, once (general inverse: a scaled <visual><origin> is not rigid)
         self._mesh_from_link = self.offset_transforms.inverse().get_matrix()
         self.sdf: typing.Optional[sdf.ComposedSDF] = sdf.ComposedSDF(link_sdfs, None)
+        self._fk_plan = self._make_fk_plan()
         self.set_joint_configuration(default_joint_config)
+
+    #: set False to force the eager forward_kinematics of the chain object (what foreign pk chains always get)
+    native_fk = True
+
+    def _make_fk_plan(self):
+        """(pvb_fk_frame[], pvb_fk_link[]) for pvb_fk_serial when the chain is this package's SerialChain in
+        float32 on a CUDA device; None otherwise (duck-typed pytorch_kinematics chains keep their own FK)."""
+        from . import _native as nat
+        from .kinematics import SerialChain
+        if not isinstance(self.chain, SerialChain) or self.dtype != torch.float32 or \
+                torch.device(self.device).type != "cuda" or not (1 <= len(self.sdf_to_link_name) <= nat.FK_MAX_LINKS):
+            return None
+        frames = self.chain.native_fk_frames()
+        if frames is None:
+            return None
+        frame_of = {f.link.name: i for i, f in enumerate(self.chain._frames)}
+        inv = self._mesh_from_link.detach().to("cpu", torch.float32)
+        if not bool((inv[:, 3] == torch.tensor([0.0, 0.0, 0.0, 1.0])).all()):
+            return None                       # a projective visual offset: not an [A | t] matrix
+        order = sorted(range(len(self.sdf_to_link_name)), key=lambda s: frame_of[self.sdf_to_link_name[s]])
+        links = (nat.FkLink * len(order))()
+        for k, s_idx in enumerate(order):
+            for r in range(3):
+                for c in range(4):
+                    links[k].mesh_from_link[4 * r + c] = float(inv[s_idx, r, c])
+            links[k].frame = frame_of[self.sdf_to_link_name[s_idx]]
+            links[k].slot = s_idx
+        return frames, links
 
     # ------------------------------------------------------------------ state
     def set_joint_configuration(self, joint_config=None):
@@ -79,6 +108,23 @@ class RobotSDF(sdf.ObjectFrameSDF):
             self.configuration_batch = torch.Size(self.configuration_batch)
         flat_q = joint_config.reshape(-1, n_joints) if batched else joint_config
         self.q = flat_q
+        if self.native_fk and self._fk_plan is not None:
+            # one kernel: FK along the chain + (FK @ visual_offset)^-1 per mesh link, written link-major
+            from . import _native as nat
+            import ctypes
+            frames, links = self._fk_plan
+            dev = nat.compute_device(self.device)
+            with torch.cuda.device(dev):
+                qd = flat_q.detach().reshape(-1, n_joints).to(device=dev, dtype=torch.float32).contiguous()
+                n_cfg = qd.shape[0]
+                out = torch.empty(len(links) * n_cfg, 4, 4, dtype=torch.float32, device=dev)
+                nat.check(nat.lib().pvb_fk_serial(ctypes.cast(frames, ctypes.c_void_p), len(frames),
+                                                  ctypes.cast(links, ctypes.c_void_p), len(links), nat.ptr(qd), n_cfg,
+                                                  n_joints, nat.ptr(out), nat.stream_ptr(dev)), "pvb_fk_serial")
+            self.object_to_link_frames = Transform3d(matrix=out)
+            if self.sdf is not None:
+                self.sdf.set_transforms(self.object_to_link_frames, batch_dim=self.configuration_batch)
+            return
         poses = self.chain.forward_kinematics(flat_q, end_only=False)
         world_from_link = torch.stack([matrix_of(poses[name]) for name in self.sdf_to_link_name])   # (S, |A|, 4, 4)
         n_links, n_cfg = world_from_link.shape[:2]

@@ -262,3 +262,64 @@ def test_robot_arm_batched_equals_looped(tmp_path):
                                         g_ref.cpu().numpy(), [grid_spec(l) for l in s.sdf.sdfs],
                                         M.cpu().numpy(), pts.cpu().numpy())
     assert n_un == 0 and n_ex <= 1e-3 * all_val.numel(), rep
+
+
+@pytest.mark.parametrize("which", ["arm", "wrench"])
+def test_native_fk_equals_eager_and_oracle(tmp_path, which):
+    """pvb_fk_serial (one kernel: chain walk + (FK @ visual_offset)^-1 per mesh link) against the eager
+    forward_kinematics path of the same chain and against the oracle's pytorch_kinematics restatement
+    (model_to_sdf.py:99-113): revolute-only arm with visual offsets, and the mixed prismatic / revolute wrench chain."""
+    import pytorch_volumetric_b200 as pv
+    from oracle import port, tp_pytorch_kinematics as opk
+    if which == "arm":
+        urdf, end = workloads.write_arm(str(tmp_path))
+        th = workloads.arm_configurations(37)
+    else:
+        urdf, end = write_wrench_urdf(str(tmp_path)), "offset_wrench"
+        th = torch.randn(37, 6, generator=torch.Generator().manual_seed(0)) * 0.4
+    chain = pv.build_serial_chain_from_urdf(open(urdf).read(), end).to(device="cuda")
+    rs = pv.RobotSDF(chain, path_prefix=str(tmp_path))            # MeshSDF links: no tables to build
+    assert rs._fk_plan is not None
+    rs.set_joint_configuration(th.cuda())
+    m_native = rs.object_to_link_frames.get_matrix().clone()
+    assert m_native.shape == (len(rs.sdf.sdfs) * 37, 4, 4)
+    rs.native_fk = False
+    rs.set_joint_configuration(th.cuda())
+    m_eager = rs.object_to_link_frames.get_matrix()
+    assert (m_native - m_eager).abs().max() < 2e-6
+    ochain = opk.build_serial_chain_from_urdf(open(urdf).read(), end)
+    ref = port.RobotSDFPort(ochain, path_prefix=str(tmp_path), link_sdf_factory=lambda mesh: port.MeshSDFPort(mesh))
+    ref.set_joint_configuration(th)
+    np.testing.assert_allclose(m_native.cpu().numpy(), ref.object_to_link.get_matrix().numpy(), atol=2e-6)
+    # single configuration (no batch): same rows as the batch, bit for bit (per-thread arithmetic)
+    rs.native_fk = True
+    rs.set_joint_configuration(th[5].cuda())
+    assert rs.configuration_batch is None
+    one = rs.object_to_link_frames.get_matrix()
+    assert torch.equal(one, m_native.view(-1, 37, 4, 4)[:, 5])
+    # multi-dimensional configuration batch
+    rs.set_joint_configuration(th[:36].view(4, 9, -1).cuda())
+    assert tuple(rs.configuration_batch) == (4, 9)
+    assert torch.equal(rs.object_to_link_frames.get_matrix().view(-1, 36, 4, 4), m_native.view(-1, 37, 4, 4)[:, :36])
+
+
+def test_robot_kernel_equals_point_major_and_ragged(tmp_path):
+    """robot_query_kernel (configuration-major, unrolled links, row epilogue) == the point-major composed kernel, bit
+    for bit incl. the argmin index, on full and ragged shapes: n_pts % 4 != 0 (scalar rows), n_pts % 32 != 0 (tail
+    tile), partial configuration tiles, and an unaligned point buffer."""
+    import pytorch_volumetric_b200 as pv
+    urdf, end = workloads.write_arm(str(tmp_path))
+    chain = pv.build_serial_chain_from_urdf(open(urdf).read(), end).to(device="cuda")
+    s = pv.RobotSDF(chain, path_prefix=str(tmp_path),
+                    link_sdf_cls=pv.cache_link_sdf_factory(resolution=0.02, padding=1.0, device="cuda",
+                                                           cache_path=str(tmp_path / "arm.pkl")))
+    lo = [r[0] for r in workloads.ARM_QUERY_RANGE]; hi = [r[1] for r in workloads.ARM_QUERY_RANGE]
+    base = workloads.uniform_points(4200, lo, hi, seed=9).cuda()
+    for n_cfg, n_pts, shift in ((64, 4096, 0), (40, 4100, 0), (33, 1001, 0), (32, 2048, 1)):
+        s.set_joint_configuration(workloads.arm_configurations(n_cfg).cuda())
+        pts = base.reshape(-1)[3 * shift:3 * (shift + n_pts)].view(n_pts, 3)       # shift=1: not 16-byte aligned
+        v, g, w = s.sdf.query(pts, return_which=True)                               # >= 16 configurations: robot kernel
+        for i in (0, n_cfg // 2, n_cfg - 1):
+            v1, g1, w1 = s.sdf.query(pts, cfg_begin=i, cfg_count=1, return_which=True)     # point-major kernel
+            sl = slice(i * n_pts, (i + 1) * n_pts)
+            assert torch.equal(v1, v[sl]) and torch.equal(g1, g[sl]) and torch.equal(w1, w[sl]), (n_cfg, n_pts, i)
