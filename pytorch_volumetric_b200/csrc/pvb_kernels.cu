@@ -950,8 +950,11 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
 #define PVB_ROBOT_PTS 4       // points per thread (4 or 2)
 #endif
 #ifndef PVB_ROBOT_MINB
-#define PVB_ROBOT_MINB 4      // resident CTAs per SM the unrolled instantiation is compiled for (register budget)
+#define PVB_ROBOT_MINB 4      // resident CTAs per SM the <= 8-link instantiation is compiled for (register budget)
 #endif
+#ifndef PVB_ROBOT_UNROLL
+#define PVB_ROBOT_UNROLL 0    // 1: fully unrolled link loop (descriptor fields become immediates, but the 8 x kRbPts inlined
+#endif                        // visits overflow the instruction cache: measured 1.61 ms against 0.87 ms, profiles/r02/)
 constexpr int kRbCfg = 32;                        // lanes = configurations
 constexpr int kRbWarps = 8;
 constexpr int kRbPts = PVB_ROBOT_PTS;             // points per thread
@@ -1126,7 +1129,7 @@ robot_query_kernel(const __grid_constant__ RobotPack<MAXS> pk, int n_sdf, const 
                 }
             }
         };
-        if constexpr (kUnroll) {
+        if constexpr (kUnroll && PVB_ROBOT_UNROLL) {
 #pragma unroll
             for (int si = 0; si < MAXS; ++si) {
                 if (si < n_sdf) link(si);
@@ -1135,8 +1138,7 @@ robot_query_kernel(const __grid_constant__ RobotPack<MAXS> pk, int n_sdf, const 
 #pragma unroll 1
             for (int si = 0; si < n_sdf; ++si) link(si);
         }
-        // ---- winning gradients back to the object frame (g @ M[:3,:3]); park the thread's 4 values + 12 gradient
-        // floats as 4 x STS.128 into the row-major staging tile ----
+        // ---- winning gradients back to the object frame (g @ M[:3,:3]) ----
         float gout[3 * kRbPts];
 #pragma unroll
         for (int k = 0; k < kRbPts; ++k) {
@@ -1148,6 +1150,48 @@ robot_query_kernel(const __grid_constant__ RobotPack<MAXS> pk, int n_sdf, const 
             const f3 go = composed_rotate_back(sm.xf[lane][3 * sb], sm.xf[lane][3 * sb + 1], sm.xf[lane][3 * sb + 2], bg[k]);
             gout[3 * k] = go.x; gout[3 * k + 1] = go.y; gout[3 * k + 2] = go.z;
         }
+        if (out_which) {            // diagnostic output (tests): strided, not on the fast path
+#pragma unroll
+            for (int k = 0; k < kRbPts; ++k)
+                if (on_mask & (1u << k)) out_which[(size_t)(c0 + lane) * n_pts + pt0 + k] = bs[k];
+        }
+        if constexpr (kDest == 0) {
+            // One destination in local memory: every lane owns kRbPts consecutive points of its configuration's row,
+            // 16 B of values + 48 B of gradients, and stores them itself -- no staging, no block barrier in the tile
+            // loop (the barriers of the staged path were 29 % of the warps' time: warps of a block finish their points
+            // at different moments).  The 16-byte pieces of neighbouring warps complete each other's sectors in L2.
+            const size_t o = (size_t)(c0 + lane) * n_pts + pt0;
+            if (vec && full_tile) {
+                if (lane_on) {
+                    if constexpr (kRbPts == 4) {
+                        __stcs(reinterpret_cast<float4 *>(out_val + o), make_float4(best[0], best[1], best[2], best[3]));
+                        float4 *dg = reinterpret_cast<float4 *>(out_grad + 3 * o);
+                        __stcs(dg, make_float4(gout[0], gout[1], gout[2], gout[3]));
+                        __stcs(dg + 1, make_float4(gout[4], gout[5], gout[6], gout[7]));
+                        __stcs(dg + 2, make_float4(gout[8], gout[9], gout[10], gout[11]));
+                    } else {
+                        __stcs(reinterpret_cast<float2 *>(out_val + o), make_float2(best[0], best[1]));
+                        float2 *dg = reinterpret_cast<float2 *>(out_grad + 3 * o);
+                        __stcs(dg, make_float2(gout[0], gout[1]));
+                        __stcs(dg + 1, make_float2(gout[2], gout[3]));
+                        __stcs(dg + 2, make_float2(gout[4], gout[5]));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kRbPts; ++k) {
+                    if (on_mask & (1u << k)) {
+                        __stcs(out_val + o + k, best[k]);
+                        __stcs(out_grad + 3 * (o + k), gout[3 * k]);
+                        __stcs(out_grad + 3 * (o + k) + 1, gout[3 * k + 1]);
+                        __stcs(out_grad + 3 * (o + k) + 2, gout[3 * k + 2]);
+                    }
+                }
+            }
+            continue;
+        }
+        // ---- several destinations / multicast: park the thread's values + gradient floats in the row-major staging
+        // tile so that every destination receives whole 512-byte rows ----
         if constexpr (kRbPts == 4) {
             *reinterpret_cast<float4 *>(&sm.outv[lane][warp * kRbPts]) = make_float4(best[0], best[1], best[2], best[3]);
             float4 *dg = reinterpret_cast<float4 *>(&sm.outg[lane][3 * warp * kRbPts]);
@@ -1160,11 +1204,6 @@ robot_query_kernel(const __grid_constant__ RobotPack<MAXS> pk, int n_sdf, const 
             dg[0] = make_float2(gout[0], gout[1]);
             dg[1] = make_float2(gout[2], gout[3]);
             dg[2] = make_float2(gout[4], gout[5]);
-        }
-        if (out_which) {            // diagnostic output (tests): strided, not on the fast path
-#pragma unroll
-            for (int k = 0; k < kRbPts; ++k)
-                if (on_mask & (1u << k)) out_which[(size_t)(c0 + lane) * n_pts + pt0 + k] = bs[k];
         }
         __syncthreads();
         if (vec && full_tile) {

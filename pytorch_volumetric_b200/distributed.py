@@ -153,13 +153,19 @@ class PeerResult:
 
     SLOTS = 2
 
-    def __init__(self, n_cfg, n_pts, group=None):
+    def __init__(self, n_cfg, n_pts, group=None, backend="auto"):
+        """backend: "ipc" = cudaMalloc + CUDA IPC handles (pvb_ipc_*); "symm" = torch symmetric memory (CUDA VMM
+        allocations exchanged by torch.distributed), which additionally yields an NVLS MULTICAST mapping of the
+        buffers when the NVSwitch fabric supports it (`self.multicast`); "auto" = symm when it works on every rank,
+        else ipc."""
         from . import _native as nat
         self.nat = nat
         self.group = group
         self.rank, self.world = _world(group)
         if self.world > nat.MAX_TARGETS:
             raise ValueError(f"PeerResult supports up to {nat.MAX_TARGETS} ranks, got {self.world}")
+        if backend not in ("auto", "ipc", "symm"):
+            raise ValueError(f"backend must be 'auto', 'ipc' or 'symm', got {backend!r}")
         self.n_cfg, self.n_pts = int(n_cfg), int(n_pts)
         n = self.n_cfg * self.n_pts
         self._grad_offset = (4 * n + 255) // 256 * 256          # value block first, gradient block 256-B aligned
@@ -168,6 +174,34 @@ class PeerResult:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self._peer_ptrs = {}
         self._local = ctypes.c_void_p()
+        self._symm = None               # (tensor, handle) of the symmetric-memory backend
+        self._mc_base = 0
+        self.backend = None
+        self.backend_note = None
+        bases = None
+        if backend in ("auto", "symm") and self.world > 1:
+            bases = self._init_symm(group)
+            if bases is None and backend == "symm":
+                raise RuntimeError(f"PeerResult(backend='symm'): {self.backend_note}")
+        if bases is None:
+            bases = self._init_ipc(group)
+        self._bases = bases
+        # own buffer first, then the peers in ring order: at any moment the ranks target different destinations
+        self._order = [(self.rank + k) % self.world for k in range(self.world)]
+        self._vals, self._grads, self._targets = [], [], []
+        for slot in range(self.SLOTS):
+            off = slot * self._slot_bytes
+            self._vals.append(torch.as_tensor(_DeviceSpan(bases[self.rank] + off, n, self),
+                                              device=self.device).view(self.n_cfg, self.n_pts))
+            self._grads.append(torch.as_tensor(_DeviceSpan(bases[self.rank] + off + self._grad_offset, 3 * n, self),
+                                               device=self.device).view(self.n_cfg, self.n_pts, 3))
+            self._targets.append([(bases[r] + off, bases[r] + off + self._grad_offset) for r in self._order])
+        self._slot = self.SLOTS - 1
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._closed = False
+
+    def _init_ipc(self, group):
+        nat = self.nat
         with torch.cuda.device(self.device):
             nat.check(nat.lib().pvb_ipc_alloc(self.nbytes, ctypes.byref(self._local)), "pvb_ipc_alloc")
             bases = [None] * self.world
@@ -184,20 +218,47 @@ class PeerResult:
                     nat.check(nat.lib().pvb_ipc_open(handles[r], ctypes.byref(mapped)), "pvb_ipc_open")
                     self._peer_ptrs[r] = mapped.value
                     bases[r] = mapped.value
-        self._bases = bases
-        # own buffer first, then the peers in ring order: at any moment the ranks target different destinations
-        self._order = [(self.rank + k) % self.world for k in range(self.world)]
-        self._vals, self._grads, self._targets = [], [], []
-        for slot in range(self.SLOTS):
-            off = slot * self._slot_bytes
-            self._vals.append(torch.as_tensor(_DeviceSpan(bases[self.rank] + off, n, self),
-                                              device=self.device).view(self.n_cfg, self.n_pts))
-            self._grads.append(torch.as_tensor(_DeviceSpan(bases[self.rank] + off + self._grad_offset, 3 * n, self),
-                                               device=self.device).view(self.n_cfg, self.n_pts, 3))
-            self._targets.append([(bases[r] + off, bases[r] + off + self._grad_offset) for r in self._order])
-        self._slot = self.SLOTS - 1
-        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
-        self._closed = False
+        self.backend = "ipc"
+        return bases
+
+    def _init_symm(self, group):
+        """torch symmetric memory: peer-mapped addresses of every rank's buffer and, on an NVSwitch fabric, one
+        multicast address that aliases all of them.  Collective; returns None (with the reason in backend_note) when
+        any rank cannot set it up."""
+        bases, err = None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            t = symm_mem.empty(self.nbytes // 4, dtype=torch.float32, device=self.device)
+            hdl = symm_mem.rendezvous(t, group=grp)
+            bases = [int(p) for p in hdl.buffer_ptrs]
+            if len(bases) != self.world or bases[self.rank] != t.data_ptr():
+                raise RuntimeError("unexpected buffer_ptrs from the symmetric memory handle")
+            self._symm = (t, hdl)
+            self._mc_base = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
+        except Exception as e:      # noqa: BLE001 -- any failure means "not available here"
+            err = f"{type(e).__name__}: {e}"[:300]
+            bases = None
+        ok = torch.tensor([0.0 if bases is None else 1.0, 1.0 if self._mc_base else 0.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok[0].item() == 0.0:
+            self._symm, self._mc_base = None, 0
+            self.backend_note = err or "another rank could not set up symmetric memory"
+            return None
+        if ok[1].item() == 0.0:
+            self._mc_base = 0
+        self.backend = "symm"
+        return bases
+
+    @property
+    def multicast(self):
+        """True when one multimem.st per chunk reaches every rank's buffer (NVLS multicast mapping available)."""
+        return self._mc_base != 0
+
+    def multicast_target(self):
+        """(val, grad) multicast addresses of the slot of the most recent next_slot() call."""
+        off = self._slot * self._slot_bytes
+        return self._mc_base + off, self._mc_base + off + self._grad_offset
 
     # the slot of the most recent query
     @property
@@ -238,7 +299,10 @@ class PeerResult:
             if self.world > 1:
                 dist.barrier(group=self.group)
             self._vals = self._grads = None
-            self.nat.check(self.nat.lib().pvb_ipc_free(self._local), "pvb_ipc_free")
+            if self._symm is not None:
+                self._symm = None           # the symmetric allocation is released with its tensor
+            else:
+                self.nat.check(self.nat.lib().pvb_ipc_free(self._local), "pvb_ipc_free")
 
 
 def sharded_robot_query(robot_sdf, points, gather=True, group=None, result=None):
@@ -255,11 +319,18 @@ def sharded_robot_query(robot_sdf, points, gather=True, group=None, result=None)
     begin, end = shard_range(n_cfg, rank, world)
     P = points.reshape(-1, 3).shape[0]
     if isinstance(gather, str):
-        if gather != "peer" or result is None:
-            raise ValueError('gather must be True, False or "peer" (the latter with result=PeerResult(...))')
+        if gather not in ("peer", "multicast") or result is None:
+            raise ValueError('gather must be True, False, "peer" or "multicast" (the latter two with '
+                             'result=PeerResult(...))')
         if (result.n_cfg, result.n_pts) != (n_cfg, P):
             raise ValueError(f"PeerResult is ({result.n_cfg}, {result.n_pts}), the query is ({n_cfg}, {P})")
-        comp.query_into(points, result.next_slot(), cfg_begin=begin, cfg_count=end - begin)
+        targets = result.next_slot()
+        if gather == "multicast":
+            if not result.multicast:
+                raise RuntimeError("this PeerResult has no multicast mapping (needs backend='symm' on an NVSwitch fabric)")
+            comp.query_multicast(points, *result.multicast_target(), cfg_begin=begin, cfg_count=end - begin)
+        else:
+            comp.query_into(points, targets, cfg_begin=begin, cfg_count=end - begin)
         result.publish()
         lead = tuple(points.shape[:-1])
         batch = tuple(comp.tsf_batch) if comp.tsf_batch is not None else ()

@@ -609,6 +609,28 @@ class ComposedSDF(ObjectFrameSDF):
                                                          ctypes.cast(arr, ctypes.c_void_p), len(targets), None,
                                                          nat.stream_ptr(device)), "pvb_composed_query_multi")
 
+    def query_multicast(self, points_in_object_frame, mc_val, mc_grad, cfg_begin=0, cfg_count=None):
+        """`query` whose result slab leaves through an NVLS multicast mapping (pvb_composed_query_multicast): mc_val /
+        mc_grad are the multicast device addresses of the full (n_cfg * P) value / gradient buffers; one multimem.st
+        per 16-byte chunk lands in every bound GPU's copy."""
+        S = len(self.sdfs)
+        n_cfg = 1 if self.tsf_batch is None else math.prod(list(self.tsf_batch))
+        if cfg_count is None:
+            cfg_count = n_cfg - cfg_begin
+        device = nat.compute_device(points_in_object_frame.device if torch.is_tensor(points_in_object_frame) else None)
+        with torch.cuda.device(device):
+            p = nat.as_f32_points(points_in_object_frame, device)
+            P = p.shape[0]
+            descs_arr, needs_mesh = self._native_descs(device)
+            if descs_arr is None:
+                raise NotImplementedError("query_multicast needs sub-SDFs with native descriptors")
+            xf = self._xforms_on(device)
+            nat.check(nat.lib().pvb_composed_query_multicast(descs_arr, S, int(needs_mesh), nat.ptr(xf), n_cfg, cfg_begin,
+                                                             cfg_count, nat.ptr(p), P, nat.PVB_MESH_DEFAULT,
+                                                             int(mc_val) + 4 * cfg_begin * P,
+                                                             int(mc_grad) + 12 * cfg_begin * P,
+                                                             nat.stream_ptr(device)), "pvb_composed_query_multicast")
+
     def _generic_query(self, p, cfg_begin, cfg_count, n_cfg, return_which):
         """Sub-SDFs without a native descriptor (user subclasses, nested compositions): per-SDF evaluation through
         their own __call__, with the transform and the running min still on the GPU."""
@@ -701,6 +723,33 @@ def grid_prune_margin(values, lo, hi, bb):
     return 0.5 * math.sqrt(sum(r * r for r in cell)) + t + 1e-5
 
 
+class _TableStore:
+    """The on-disk table cache of CachedSDF: one torch.save file holding {name: (val[nx,ny,nz], grad[Nvox,3])} for any
+    number of objects -- the layout of the reference's sdf_cache.pkl (sdf.py:487-519), so existing files keep
+    loading and files written here load in the reference."""
+
+    def __init__(self, path):
+        self.path = path
+        self.entries = (torch.load(path) or {}) if os.path.exists(path) else {}
+
+    def get(self, name):
+        entry = self.entries.get(name)
+        if entry is None:
+            return None
+        try:
+            val, grad = entry
+        except (ValueError, TypeError):
+            logger.info("cached sdf invalid %s from %s, recreating", name, self.path)
+            return None
+        logger.info("cached sdf for %s loaded from %s", name, self.path)
+        return val, grad
+
+    def put(self, name, tables):
+        self.entries[name] = tuple(t.cpu() for t in tables)
+        torch.save(self.entries, self.path)
+        logger.info("caching sdf for %s to %s", name, self.path)
+
+
 class CachedSDF(ObjectFrameSDF):
     """SDF via nearest-voxel lookup of precomputed value and gradient tables."""
 
@@ -733,45 +782,24 @@ class CachedSDF(ObjectFrameSDF):
         self.resolution = resolution
         self._cdev = nat.compute_device(device)
 
-        cached_underlying_sdf = None
-        cached_underlying_sdf_grad = None
-
-        bb = np.array(range_per_dim)
-        r = bb[:, 1] - bb[:, 0]
-        num_voxel = r // resolution
-        if min(num_voxel) < 10:
-            logger.warning(f"Resolution {resolution} is too high for {object_name}, only getting {num_voxel} voxels.")
-
-        range_per_dim = get_divisible_range_by_resolution(resolution, range_per_dim)
-        self.ranges = range_per_dim
-        self.name = f"{object_name} {resolution} {tuple(range_per_dim)}"
+        span = np.asarray(range_per_dim, dtype=np.float64)
+        cells = (span[:, 1] - span[:, 0]) // resolution
+        if cells.min() < 10:
+            logger.warning(f"Resolution {resolution} is too high for {object_name}, only getting {cells} voxels.")
+        self.ranges = get_divisible_range_by_resolution(resolution, range_per_dim)
+        range_per_dim = self.ranges
+        # cache key: name, resolution and the snapped range, the format existing sdf_cache.pkl files were written with
+        self.name = f"{object_name} {resolution} {tuple(self.ranges)}"
         self.debug_check_sdf = debug_check_sdf
 
-        if os.path.exists(cache_path):
-            data = torch.load(cache_path) or {}
-            try:
-                cached_underlying_sdf, cached_underlying_sdf_grad = data[self.name]
-                logger.info("cached sdf for %s loaded from %s", self.name, cache_path)
-            except (ValueError, KeyError):
-                logger.info("cached sdf invalid %s from %s, recreating", self.name, cache_path)
-        else:
-            data = {}
-
-        if cached_underlying_sdf is None or clean_cache:
+        store = _TableStore(cache_path)
+        tables = None if clean_cache else store.get(self.name)
+        if tables is None:
             if gt_sdf is None:
                 raise RuntimeError("Cached SDF did not find the cache and requires an initialize queryable SDF")
-            coords, pts = get_coordinates_and_points_in_grid(self.resolution, self.ranges)
-            # table build = one batched ground-truth query over every voxel centre, on the GPU
-            sdf_val, sdf_grad = gt_sdf(pts.to(self._cdev))
-            cached_underlying_sdf = sdf_val.reshape([len(coord) for coord in coords])
-            cached_underlying_sdf_grad = sdf_grad.squeeze(0)
-            if self.debug_check_sdf:
-                debug_view = GridView(cached_underlying_sdf, self.ranges, invalid_value=self._fallback_sdf_value_func)
-                query = debug_view[pts.to(cached_underlying_sdf.device)]
-                assert torch.allclose(sdf_val.reshape(-1), query.reshape(-1))
-            data[self.name] = cached_underlying_sdf.cpu(), cached_underlying_sdf_grad.cpu()
-            torch.save(data, cache_path)
-            logger.info("caching sdf for %s to %s", self.name, cache_path)
+            tables = self._build_tables(gt_sdf)
+            store.put(self.name, tables)
+        cached_underlying_sdf, cached_underlying_sdf_grad = tables
 
         val = cached_underlying_sdf.to(device=self._cdev, dtype=torch.float32)
         grad = cached_underlying_sdf_grad.to(device=self._cdev, dtype=torch.float32).reshape(-1, 3)
@@ -781,6 +809,19 @@ class CachedSDF(ObjectFrameSDF):
         self._table = torch.cat([val.reshape(-1, 1), grad], dim=1).contiguous()
         self.bb = self.surface_bounding_box().to(device=self._cdev)
         self._desc = self._make_desc()
+
+    def _build_tables(self, gt_sdf):
+        """(val[nx,ny,nz], grad[Nvox,3]): ONE batched ground-truth query over every voxel centre, on the GPU
+        (the reference evaluates the same points through its CPU MeshSDF, sdf.py:502-505)."""
+        coords, pts = get_coordinates_and_points_in_grid(self.resolution, self.ranges)
+        sdf_val, sdf_grad = gt_sdf(pts.to(self._cdev))
+        val = sdf_val.reshape([len(coord) for coord in coords])
+        grad = sdf_grad.squeeze(0)
+        if self.debug_check_sdf:
+            debug_view = GridView(val, self.ranges, invalid_value=self._fallback_sdf_value_func)
+            query = debug_view[pts.to(val.device)]
+            assert torch.allclose(sdf_val.reshape(-1), query.reshape(-1))
+        return val, grad
 
     # -- descriptor -----------------------------------------------------------------
     def _make_desc(self):
@@ -1010,20 +1051,16 @@ def sample_mesh_points(obj_factory: ObjectFactory = None, num_points=100, seed=0
     actual point set for a given seed differs from Open3D's mt19937 stream (the reference's stream is not
     reproducible outside Open3D either); it is deterministic per (mesh, seed, num_points).
     """
-    given_cache = cache is not None
-    if cache is not None or os.path.exists(dbpath):
-        if cache is None:
-            cache = torch.load(dbpath)
-        if name not in cache:
-            cache[name] = {}
-        if seed not in cache[name]:
-            cache[name][seed] = {}
-        if not clean_cache and num_points in cache[name][seed]:
-            res = cache[name][seed][num_points]
-            res = list(v.to(device=device, dtype=dtype) if v is not None else None for v in res)
-            return *res[:-1], cache
-    else:
-        cache = {name: {seed: {}}}
+    # cache layout of the reference (sdf.py:620-634, 665): {name: {seed: {num_points: (points, normals, None)}}}, kept in
+    # the caller's dict when one is passed, otherwise in the torch.save file `dbpath`
+    caller_owns_cache = cache is not None
+    if cache is None:
+        cache = torch.load(dbpath) if os.path.exists(dbpath) else {}
+    per_count = cache.setdefault(name, {}).setdefault(seed, {})
+    hit = None if clean_cache else per_count.get(num_points)
+    if hit is not None:
+        points, normals = (None if t is None else t.to(device=device, dtype=dtype) for t in hit[:2])
+        return points, normals, cache
 
     if obj_factory is None:
         raise RuntimeError(f"Expect model points to be cached for {name} {seed} {num_points} in {dbpath}")
@@ -1041,8 +1078,8 @@ def sample_mesh_points(obj_factory: ObjectFactory = None, num_points=100, seed=0
     res = obj_factory.object_frame_closest_point(points, compute_normal=True)   # sdf.py:660
     normals = res.normal
 
-    cache[name][seed][num_points] = points.cpu(), normals.cpu(), None
-    if not given_cache:
+    per_count[num_points] = points.cpu(), normals.cpu(), None
+    if not caller_owns_cache:
         torch.save(cache, dbpath)
     return points.to(device=device, dtype=dtype), normals.to(device=device, dtype=dtype), cache
 
