@@ -13,7 +13,8 @@ DEFAULT (no --workload): the line the driver records.
     and the timed step ends with the FULL (200, 100 000) result on EVERY rank -- re-assembly inside the timed
     region.  `value` = 2*10^7 (configuration, point) pairs / max-over-ranks device time.  The `reassembly` object
     carries the sub-values next to it: no_reassembly (every rank keeps its slab), nccl_all_gather, peer_stores
-    (kernel epilogue stores into all ranks' buffers over NVLink), each timed the same way.
+    (kernel epilogue stores into all ranks' buffers over NVLink), multicast_stores (one multimem.st per chunk through
+    an NVLS multicast mapping), each timed the same way.
   * `workloads`: every other BASELINE config on the same GPUs in the same run -- mesh10k (the north-star
     single-GPU target: MeshSDF on a 10 000-triangle mesh, 10^7 queries), c2, c3, c3cached, c5 -- each with value,
     ms_per_step, roofline{achieved, frac, traffic, kernel_ms}, e2e and (N=1) cpu_baseline.
@@ -294,8 +295,8 @@ def c4_config(n_cfg=200, n_pts=100_000):
                         f"ranks, full ({n_cfg}, {n_pts}) result on every rank inside the timed region",
             "n_cfg": n_cfg, "n_pts": n_pts, "units_per_step": n_cfg * n_pts,
             "l2_policy": "output 320 MB/step > L2 (126 MB); 3 rotating point buffers",
-            "result_reassembly": "full result on every rank; method = the faster of NCCL all-gather / peer stores "
-                                 "measured in this run (reassembly.chosen); no collective at N=1"}
+            "result_reassembly": "full result on every rank; method = the fastest of NCCL all-gather / peer stores / "
+                                 "multicast stores measured in this run (reassembly.chosen); no collective at N=1"}
 
 
 class C4(Workload):
@@ -367,6 +368,8 @@ class C4(Workload):
             return self.robot(pts)                                 # the public RobotSDF.__call__
         if self.mode == "peer":   # full result on every rank, written by the kernels themselves
             return self.pd.sharded_robot_query(self.robot, pts, gather="peer", result=self.peer)
+        if self.mode == "mc":     # ... through the NVLS multicast mapping: one multimem.st reaches every rank
+            return self.pd.sharded_robot_query(self.robot, pts, gather="multicast", result=self.peer)
         if self.mode == "nccl":   # full result on every rank: one NCCL all-gather per tensor
             return self.pd.sharded_robot_query(self.robot, pts, gather=True)
         return self.pd.sharded_robot_query(self.robot, pts, gather=False)
@@ -821,7 +824,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="default run: headline only")
-    ap.add_argument("--mode", default=None, choices=[None, "none", "nccl", "peer"],
+    ap.add_argument("--mode", default=None, choices=[None, "none", "nccl", "peer", "mc"],
                     help="C4 at N>1: force the re-assembly method of the headline instead of picking the faster one")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -876,10 +879,20 @@ def main():
             remote = 16.0 * wl.units * (world - 1)          # bytes this rank pushes to its peers per step
             reassembly["peer_stores"] = {"ms_per_step": ms / sub_steps, "value": units_all * sub_steps / (ms * 1e-3),
                                          "nvlink_out_GBps_per_rank": remote / (ms / sub_steps * 1e-3) / 1e9,
-                                         "nvlink_in_bytes_per_rank": remote}
+                                         "nvlink_in_bytes_per_rank": remote, "buffers": wl.peer.backend}
+            if wl.peer.multicast:
+                wl.set_mode("mc")
+                ms, _, _ = timed_steps(wl.step, sub_steps, args.warmup, world)
+                reassembly["multicast_stores"] = {"ms_per_step": ms / sub_steps,
+                                                  "value": units_all * sub_steps / (ms * 1e-3),
+                                                  "nvlink_out_GBps_per_rank": 16.0 * wl.units / (ms / sub_steps * 1e-3) / 1e9}
+            else:
+                reassembly["multicast_stores"] = {"unavailable": wl.peer.backend_note or
+                                                  f"no multicast mapping (buffers: {wl.peer.backend})"}
         else:
             reassembly["peer_stores"] = {"unavailable": err}
-        for k in ("nccl_all_gather", "peer_stores"):
+            reassembly["multicast_stores"] = {"unavailable": err}
+        for k in ("nccl_all_gather", "peer_stores", "multicast_stores"):
             if "ms_per_step" in reassembly[k]:
                 reassembly[k]["nvlink_ingest_GBps_per_rank"] = \
                     16.0 * (units_all - wl.units) / (reassembly[k]["ms_per_step"] * 1e-3) / 1e9
@@ -890,10 +903,12 @@ def main():
             cands = {"nccl": reassembly["nccl_all_gather"]["ms_per_step"]}
             if "ms_per_step" in reassembly["peer_stores"]:
                 cands["peer"] = reassembly["peer_stores"]["ms_per_step"]
+            if "ms_per_step" in reassembly["multicast_stores"]:
+                cands["mc"] = reassembly["multicast_stores"]["ms_per_step"]
             chosen = min(cands, key=cands.get)
-        flag = torch.tensor([{"none": 0, "nccl": 1, "peer": 2}[chosen]], device="cuda")     # rank 0 decides
+        flag = torch.tensor([{"none": 0, "nccl": 1, "peer": 2, "mc": 3}[chosen]], device="cuda")     # rank 0 decides
         torch.distributed.broadcast(flag, src=0)
-        chosen = ("none", "nccl", "peer")[int(flag.item())]
+        chosen = ("none", "nccl", "peer", "mc")[int(flag.item())]
         reassembly["chosen"] = chosen
         wl.set_mode(chosen)
 

@@ -268,6 +268,32 @@ int pvb_chamfer(const pvb_sdf_desc *obj, const float *world_to_object, int32_t n
 int pvb_mesh_sample(const double *verts64, const int32_t *faces, int64_t n_faces, const int64_t *cum_counts,
                     int64_t n, uint64_t seed, double *out_pts, int32_t *out_face, void *stream);
 
+/* ---- voxel containers: VoxelGrid / ExpandingVoxelGrid / voxel_down_sample (voxel.py:42-171) over the value-range
+ * view TorchMultidimView (sdf.py:264; voxel.py:55-64, 88-91) ----
+ * Grid geometry: d in 1..3 coordinates per point, per-axis min64 / res64 (HOST double[d]) and dims (HOST int32[d]);
+ * fp32_mode != 0 evaluates the index in fp32 (ranges given as Python floats / float32 numpy), else in fp64 (float64
+ * numpy ranges) -- the dtype torch infers for the range tensors.  Cell of a point: round((p - min) / res), half to even
+ * like torch.round; valid when every index is in [0, dim).  Flat indices are C order (last axis fastest).
+ *   pvb_voxel_index    out_index[n] int64 flat cell or -1                       (ensure_index_key + ravel_multi_index)
+ *   pvb_voxel_scatter  data[cell(p_i)] = values[i] (values == NULL: `scalar`)   (view[pts] = value, voxel.py:90-91)
+ *   pvb_voxel_gather   out[i] = data[cell(p_i)] or `invalid`; out_valid optional (view[pts], voxel.py:87-88)
+ *   pvb_compact_nonempty  ascending flat indices of the cells with data != empty (get_known_pos_and_values,
+ *                      voxel.py:59-65; the compaction behind voxel_down_sample, voxel.py:166-167); out_count DEVICE
+ *                      int64[1] receives the number found (also when capacity is too small: call again);
+ *                      workspace DEVICE, pvb_compact_workspace(n) bytes.
+ * elem_bytes: 4 = float32 grid, 1 = bool / uint8 grid.  All pointers DEVICE unless marked HOST. */
+int pvb_voxel_index(int32_t d, const double *min64, const double *res64, const int32_t *dims, int32_t fp32_mode,
+                    const float *pts, int64_t n, int64_t *out_index, void *stream);
+int pvb_voxel_scatter(int32_t d, const double *min64, const double *res64, const int32_t *dims, int32_t fp32_mode,
+                      const float *pts, int64_t n, int32_t elem_bytes, const void *values, double scalar, void *data,
+                      void *stream);
+int pvb_voxel_gather(int32_t d, const double *min64, const double *res64, const int32_t *dims, int32_t fp32_mode,
+                     const float *pts, int64_t n, int32_t elem_bytes, const void *data, double invalid, void *out,
+                     uint8_t *out_valid, void *stream);
+int64_t pvb_compact_workspace(int64_t n);
+int pvb_compact_nonempty(const void *data, int64_t n, int32_t elem_bytes, double empty, void *workspace,
+                         int64_t capacity, int64_t *out_index, int64_t *out_count, void *stream);
+
 /* ---- rigid transform helpers used by the generic (unfused) composition path ---- */
 int pvb_transform_points(const float *xforms, int32_t n_tf, const float *pts, int64_t n_pts,
                          float *out, void *stream);

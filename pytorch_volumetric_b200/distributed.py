@@ -231,11 +231,15 @@ class PeerResult:
             grp = group if group is not None else dist.group.WORLD
             t = symm_mem.empty(self.nbytes // 4, dtype=torch.float32, device=self.device)
             hdl = symm_mem.rendezvous(t, group=grp)
-            bases = [int(p) for p in hdl.buffer_ptrs]
-            if len(bases) != self.world or bases[self.rank] != t.data_ptr():
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            # buffer_ptrs address the allocation block; the tensor may sit at an offset inside it (same on every rank)
+            off0 = t.data_ptr() - ptrs[self.rank]
+            if len(ptrs) != self.world or off0 < 0 or off0 % 256:
                 raise RuntimeError("unexpected buffer_ptrs from the symmetric memory handle")
+            bases = [p + off0 for p in ptrs]
             self._symm = (t, hdl)
-            self._mc_base = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            self._mc_base = mc + off0 if mc else 0
         except Exception as e:      # noqa: BLE001 -- any failure means "not available here"
             err = f"{type(e).__name__}: {e}"[:300]
             bases = None

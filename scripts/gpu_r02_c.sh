@@ -3,7 +3,7 @@
 set -u
 OUT=gpurun_out/r02c
 mkdir -p "$OUT"
-timeout 600 python -m pytest tests/test_gpu_composed.py tests/test_gpu_peer.py -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" >> "$OUT/pytest_gpu.log"
+timeout 1200 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" >> "$OUT/pytest_gpu.log"
 tail -5 "$OUT/pytest_gpu.log"
 PVB_LIB=$PWD/tune/libpvb_rb_r_p2m4.so timeout 600 python -m pytest tests/test_gpu_composed.py tests/test_gpu_peer.py -m gpu -x -q > "$OUT/pytest_gpu_p2.log" 2>&1; echo "pytest rc=$?" >> "$OUT/pytest_gpu_p2.log"
 tail -3 "$OUT/pytest_gpu_p2.log"
@@ -21,4 +21,12 @@ PVB_LIB=$PWD/tune/libpvb_rb_r_p2m4.so timeout 500 $NCU -k regex:robot_query -s 3
     python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > "$OUT/ncu_c4.log" 2>&1
 PVB_LIB=$PWD/tune/libpvb_rb_r_p4m3.so timeout 500 $NCU -k regex:robot_query -s 3 -c 1 -o "$OUT/c4_robot_r_p4m3" -f \
     python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > "$OUT/ncu_c4b.log" 2>&1
+for w in mesh10k c5 c3; do timeout 300 python bench.py --workload $w --steps 20 --no-cpu-baseline 2>/dev/null | grep '^{' | tail -1; done > "$OUT/bench_mesh_workloads.jsonl"
+python - <<'PY'
+import json
+for l in open("gpurun_out/r02c/bench_mesh_workloads.jsonl"):
+    d = json.loads(l); print(d["config"]["workload"][:40], "ms", round(d["ms_per_step"], 3), "kernel_ms", round(d["roofline"]["kernel_ms"], 3), "e2e", round(d["e2e"]["ms_per_step"], 2))
+PY
+timeout 500 $NCU -k regex:mesh_query_kernel -s 3 -c 1 -o "$OUT/mesh10k_v2" -f \
+    python bench.py --workload mesh10k --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > "$OUT/ncu_mesh.log" 2>&1
 ls -la "$OUT"

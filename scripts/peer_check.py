@@ -49,26 +49,58 @@ def main():
     pts = workloads.uniform_points(n_pts, lo, hi, seed=4).cuda()
 
     v_full, g_full = robot(pts)                                  # unsharded, this GPU
-    res = pd.PeerResult(n_cfg, n_pts)
-    v, g = pd.sharded_robot_query(robot, pts, gather="peer", result=res)
-    torch.cuda.synchronize()
-    ok = torch.equal(v, v_full) and torch.equal(g, g_full)
+    ok = True
+    results = {}
+    begin, endc = pd.shard_range(n_cfg, rank, world)
+
+    def check(tag, v, g):
+        torch.cuda.synchronize()
+        good = torch.equal(v, v_full) and torch.equal(g, g_full)
+        results[tag + "_bit_exact"] = bool(good)
+        return good
+
     vg, gg = pd.sharded_robot_query(robot, pts, gather=True)     # NCCL all-gather of the slabs
-    ok = ok and torch.equal(vg, v_full) and torch.equal(gg, g_full)
+    ok = check("nccl", vg, gg) and ok
+    peers = {}
+    for backend in ("ipc", "symm"):
+        try:
+            peers[backend] = pd.PeerResult(n_cfg, n_pts, backend=backend)
+        except Exception as e:      # noqa: BLE001
+            results[backend + "_unavailable"] = repr(e)[:200]
+            # every rank must take the same branch: PeerResult construction is collective and raises on all ranks
+            continue
+        res = peers[backend]
+        for rep in range(3):        # three queries: both slots and the reuse of the first
+            v, g = pd.sharded_robot_query(robot, pts, gather="peer", result=res)
+            ok = check(f"peer_{backend}_{rep}", v, g) and ok
+        if res.multicast:
+            for rep in range(3):
+                v, g = pd.sharded_robot_query(robot, pts, gather="multicast", result=res)
+                ok = check(f"multicast_{rep}", v, g) and ok
+        results[backend + "_multicast"] = bool(res.multicast)
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 
-    begin, endc = pd.shard_range(n_cfg, rank, world)
-    t_local = timed(lambda: robot.sdf.query(pts, cfg_begin=begin, cfg_count=endc - begin), steps)
-    t_nccl = timed(lambda: pd.sharded_robot_query(robot, pts, gather=True), steps)
-    t_peer = timed(lambda: pd.sharded_robot_query(robot, pts, gather="peer", result=res), steps)
-    res.close()
+    times = {"ms_no_reassembly": timed(lambda: robot.sdf.query(pts, cfg_begin=begin, cfg_count=endc - begin), steps),
+             "ms_nccl_all_gather": timed(lambda: pd.sharded_robot_query(robot, pts, gather=True), steps)}
+    for backend, res in peers.items():
+        times[f"ms_peer_stores_{backend}"] = timed(
+            lambda: pd.sharded_robot_query(robot, pts, gather="peer", result=res), steps)
+        if res.multicast:
+            times["ms_multicast_stores"] = timed(
+                lambda: pd.sharded_robot_query(robot, pts, gather="multicast", result=res), steps)
+    for res in peers.values():
+        res.close()
     if rank == 0:
         remote = 16.0 * (endc - begin) * n_pts * (world - 1)
-        print(json.dumps({"world": world, "n_cfg": n_cfg, "n_pts": n_pts, "bit_exact_all_ranks": bool(flag.item()),
-                          "ms_no_reassembly": t_local, "ms_nccl_all_gather": t_nccl, "ms_peer_stores": t_peer,
-                          "remote_bytes_per_rank": remote,
-                          "nvlink_out_GBps_per_rank": remote / (t_peer * 1e-3) / 1e9}))
+        line = {"world": world, "n_cfg": n_cfg, "n_pts": n_pts, "bit_exact_all_ranks": bool(flag.item()),
+                "remote_bytes_per_rank": remote}
+        line.update(times)
+        line.update(results)
+        for k, t in times.items():
+            if k.startswith("ms_peer") or k.startswith("ms_multicast") or k.startswith("ms_nccl"):
+                line[k.replace("ms_", "nvlink_ingest_GBps_")] = remote / (t * 1e-3) / 1e9
+        print(json.dumps(line))
         if flag.item() == 1.0:
             print("PEER_OK")
     dist.destroy_process_group()
