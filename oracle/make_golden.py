@@ -202,7 +202,78 @@ def make_reference_vectors():
         print(name, "chamfer: err0 max", float(err0.max()), "err1 mean", float(err1.mean()))
 
 
+def make_voxel_vectors():
+    """The reference's voxel containers (src/pytorch_volumetric/voxel.py:42-171) run unmodified over the shims:
+    VoxelGrid set / get / list / resize, ExpandingVoxelGrid growth, voxel_down_sample on the reference's own test
+    surface (tests/test_voxel_sdf.py:8-39) with numpy (fp32) and explicit ranges, 3-D and flat-z clouds, and
+    ObjectFrameSDF.get_filtered_points (sdf.py:273-282) of the probe's CachedSDF voxel view."""
+    pv = import_reference()
+    g = torch.Generator().manual_seed(99)
+    out = {}
+    # ---- VoxelGrid: scatter-set, gather (incl. out-of-range -> invalid 0), list, resize_to_fit ----
+    box = [(-1, 1), (-0.5, 0.5), (0, 0.6)]
+    vg = pv.VoxelGrid(0.05, box)
+    p = (torch.rand(3000, 3, generator=g) * torch.tensor([2.4, 1.3, 0.8]) + torch.tensor([-1.2, -0.65, -0.1])).float()
+    val = torch.rand(3000, generator=g) + 0.5
+    vg[p] = val
+    out["vg_box"] = np.array(box, dtype=np.float64)
+    out["vg_pts"], out["vg_val"] = p.numpy(), val.numpy()
+    q = (torch.rand(2000, 3, generator=g) * torch.tensor([2.4, 1.3, 0.8]) + torch.tensor([-1.2, -0.65, -0.1])).float()
+    out["vg_q"] = q.numpy()
+    out["vg_q_out"] = vg[q].numpy()
+    out["vg_data"] = vg.get_voxel_values().numpy()
+    pos, kv = vg.get_known_pos_and_values()
+    out["vg_known_pos"], out["vg_known_val"] = pos.numpy(), kv.numpy()
+    vg.resize_to_fit()
+    out["vg_fit_range"] = np.array(vg.range_per_dim, dtype=np.float64)
+    out["vg_fit_shape"] = np.array(vg.get_voxel_values().shape)
+    out["vg_fit_q_out"] = vg[q].numpy()
+    # ---- ExpandingVoxelGrid ----
+    ev = pv.ExpandingVoxelGrid(0.1, [(0, 1), (0, 1), (0, 1)])
+    e1 = torch.tensor([[0.5, 0.5, 0.5], [0.93, 0.12, 0.31]])
+    e2 = torch.tensor([[2.03, -0.47, 0.5], [-0.76, 1.88, 1.41]])
+    ev[e1] = torch.tensor([4.0, 5.0])
+    ev[e2] = torch.tensor([7.0, 8.0])
+    out["ev_p1"], out["ev_p2"] = e1.numpy(), e2.numpy()
+    out["ev_range"] = np.array(ev.range_per_dim, dtype=np.float64)
+    out["ev_shape"] = np.array(ev.get_voxel_values().shape)
+    out["ev_read"] = ev[torch.cat((e1, e2))].numpy()
+    # ---- voxel_down_sample: the reference's own test surface (tests/test_voxel_sdf.py:8-29) ----
+    N = 100
+    x = torch.linspace(-2, 2, N)
+    xx, yy = torch.meshgrid(x, x, indexing="ij")
+    zz = torch.sin(xx) + 2 * torch.cos(yy)
+    surf = torch.stack((xx.flatten(), yy.flatten(), zz.flatten()), dim=-1)
+    out["ds_pts"] = surf.numpy()
+    out["ds_02"] = pv.voxel_down_sample(surf, 0.2).numpy()
+    out["ds_007"] = pv.voxel_down_sample(surf, 0.07).numpy()
+    rng = np.array([[-1.0, 1.0], [-1.5, 0.5], [-3.0, 3.0]])           # does not enclose the data: honoured (voxel.py:153)
+    out["ds_range"] = rng
+    out["ds_ranged"] = pv.voxel_down_sample(surf, 0.1, range_per_dim=rng).numpy()
+    flat = torch.cat((surf[:, :2], torch.zeros(len(surf), 1)), dim=1)
+    frng = np.array([[-1.7, 1.9], [-2.5, 1.5], [0.0, 0.0]])
+    out["ds_flat_range"] = frng
+    out["ds_flat"] = pv.voxel_down_sample(flat, 0.15, range_per_dim=frng, ignore_flat_dim=True).numpy()
+    # ---- get_filtered_points of a CachedSDF voxel view (sdf.py:273-282): the interior of the probe ----
+    obj = pv.MeshObjectFactory(os.path.join(REF, MESHES["probe"]))
+    sdf = pv.MeshSDF(obj)
+    np.random.seed(5)
+    cached = pv.CachedSDF("probe", 0.002, obj.bounding_box(padding=0.01), sdf, cache_path="/tmp/pvb_golden_voxel.pkl",
+                          clean_cache=True)
+    inner = cached.get_filtered_points(lambda v: v < -0.001)
+    out["fp_interior"] = inner.numpy()
+    out["fp_table"] = cached.voxels.raw_data.numpy()
+    out["fp_shape"] = np.array(cached.voxels.shape)
+    out["fp_ranges"] = np.array(cached.ranges, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "ref_voxel.npz"), **out)
+    print("ref_voxel.npz:", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    make_meshes()
-    make_reference_vectors()
+    if len(sys.argv) > 1 and sys.argv[1] == "voxel":
+        make_voxel_vectors()
+    else:
+        make_meshes()
+        make_reference_vectors()
+        make_voxel_vectors()

@@ -47,6 +47,11 @@ class TorchMultidimView:
 
     def ensure_value_key(self, key, force=False):
         if self._is_value_range or force:
+            # flat (ravelled) indices -- what raw_data.nonzero() yields, voxel.py:60-62 -- address cells of the
+            # n-d table: pinned by the reference's own tests/test_voxel_sdf.py:25-29 (voxel_down_sample must return
+            # positions ON the sampled surface), which only holds if they are unravelled in C order first
+            if key.shape[-1] == 1 and self.dim > 1:
+                key = torch.stack(torch.unravel_index(key.reshape(-1), tuple(self.shape)), dim=-1)
             return key * self._resolution + self._min
         return key
 

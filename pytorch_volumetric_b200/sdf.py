@@ -33,7 +33,7 @@ from . import _native as nat
 from . import meshio
 from .transforms import Transform3d, matrix_of
 from .voxel import (GridView, VoxelGrid, get_coordinates_and_points_in_grid, get_divisible_range_by_resolution,
-                    range_dtype)
+                    nonempty_indices, range_dtype)
 
 logger = logging.getLogger(__name__)
 
@@ -383,7 +383,7 @@ class ObjectFrameSDF(abc.ABC):
                             device='cpu') -> torch.tensor:
         model_voxels = self.get_voxel_view(voxels, dtype=dtype, device=device)
         interior = unary_filter(model_voxels.raw_data)
-        flat = interior.nonzero().reshape(-1)
+        flat = nonempty_indices(interior.reshape(-1))
         idx = torch.stack(torch.unravel_index(flat, tuple(model_voxels.shape)), dim=-1)
         return model_voxels.ensure_value_key(idx)
 

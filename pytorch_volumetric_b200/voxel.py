@@ -8,6 +8,7 @@ path and its callers use (`raw_data`, `shape`, `ensure_index_key`,
 `ravel_multi_index`, `get_valid_values`, `ensure_value_key`, `view[pts]`).
 """
 import abc
+import ctypes
 
 import numpy as np
 import torch
@@ -36,8 +37,38 @@ def range_dtype(value_ranges):
     return torch.tensor([min(r) for r in value_ranges]).dtype
 
 
+def nonempty_indices(flat, empty=0):
+    """Ascending flat indices of the elements of a 1-D tensor that differ from `empty` -- the compaction behind
+    get_known_pos_and_values / voxel_down_sample / get_filtered_points.  float32 and bool tensors on a CUDA device go
+    through pvb_compact_nonempty (block counts, scan, ordered write); anything else is host-side torch."""
+    if flat.is_cuda and flat.dtype in (torch.float32, torch.bool, torch.uint8) and flat.is_contiguous() \
+            and 0 < flat.numel() < 2 ** 32:
+        from . import _native as nat
+        data = flat.view(torch.uint8) if flat.dtype == torch.bool else flat
+        n = data.numel()
+        dev = flat.device
+        with torch.cuda.device(dev):
+            L = nat.lib()
+            ws = torch.empty(int(L.pvb_compact_workspace(n)), dtype=torch.uint8, device=dev)
+            count = torch.zeros(1, dtype=torch.int64, device=dev)
+            eb = 4 if data.dtype == torch.float32 else 1
+            nat.check(L.pvb_compact_nonempty(nat.ptr(data), n, eb, float(empty), nat.ptr(ws), 0, None, nat.ptr(count),
+                                             nat.stream_ptr(dev)), "pvb_compact_nonempty")
+            k = int(count.item())
+            out = torch.empty(k, dtype=torch.int64, device=dev)
+            if k:
+                nat.check(L.pvb_compact_nonempty(nat.ptr(data), n, eb, float(empty), nat.ptr(ws), k, nat.ptr(out),
+                                                 nat.ptr(count), nat.stream_ptr(dev)), "pvb_compact_nonempty")
+        return out
+    return (flat != empty).nonzero().reshape(-1)
+
+
 class GridView:
-    """Dense n-d value table addressed by real-valued coordinates (nearest cell)."""
+    """Dense n-d value table addressed by real-valued coordinates (nearest cell).
+
+    Tables of float32 / bool on a CUDA device are read, written and listed by the voxel kernels of libpvb.so
+    (pvb_voxel_gather / pvb_voxel_scatter, include/pvb.h) when the points are float32; host-resident tables -- the
+    reference's default device -- are ordinary torch tensors and use torch indexing."""
 
     def __init__(self, source, value_ranges, invalid_value=-1):
         self.device = source.device
@@ -72,7 +103,48 @@ class GridView:
             flat = flat * shape[d] + key[..., d]
         return flat
 
+    # -- kernel path ---------------------------------------------------------------
+    def _native_ok(self, pts):
+        return (self._d.is_cuda and self.dim <= 3 and self._d.dtype in (torch.float32, torch.bool)
+                and torch.is_tensor(pts) and pts.dtype == torch.float32 and pts.shape[-1] == self.dim
+                and self._d.is_contiguous())
+
+    def _geom(self):
+        g = getattr(self, "_geom_cache", None)
+        if g is None:
+            lo = self._min.double().cpu().tolist()
+            res = self._resolution.double().cpu().tolist()
+            g = ((ctypes.c_double * self.dim)(*lo), (ctypes.c_double * self.dim)(*res),
+                 (ctypes.c_int32 * self.dim)(*[int(v) for v in self.shape]),
+                 1 if self._min.dtype == torch.float32 else 0)
+            self._geom_cache = g
+        return g
+
+    def _data_u8(self):
+        return self._d.view(torch.uint8) if self._d.dtype == torch.bool else self._d
+
     def __getitem__(self, pts):
+        if self._native_ok(pts):
+            from . import _native as nat
+            lead = pts.shape[:-1]
+            dev = self._d.device
+            p = pts.reshape(-1, self.dim).to(dev).contiguous()
+            n = p.shape[0]
+            lo, res, dims, f32 = self._geom()
+            data = self._data_u8()
+            out = torch.empty(n, dtype=data.dtype, device=dev)
+            fill = 0.0 if callable(self.invalid_value) else float(self.invalid_value)
+            valid = torch.empty(n, dtype=torch.uint8, device=dev) if callable(self.invalid_value) else None
+            with torch.cuda.device(dev):
+                nat.check(nat.lib().pvb_voxel_gather(self.dim, lo, res, dims, f32, nat.ptr(p), n,
+                                                     4 if data.dtype == torch.float32 else 1, nat.ptr(data), fill,
+                                                     nat.ptr(out), nat.ptr(valid), nat.stream_ptr(dev)), "pvb_voxel_gather")
+            out = out.view(torch.bool) if self._d.dtype == torch.bool else out
+            if valid is not None:
+                bad = valid == 0
+                if bool(bad.any()):
+                    out[bad] = self.invalid_value(p[bad]).to(self.dtype).reshape(-1)
+            return out.reshape(lead)
         lead = pts.shape[:-1]
         p = pts.reshape(-1, pts.shape[-1]).to(self.device)
         idx = self.ensure_index_key(p)
@@ -88,6 +160,27 @@ class GridView:
         return out.reshape(lead)
 
     def __setitem__(self, pts, value):
+        if self._native_ok(pts):
+            from . import _native as nat
+            dev = self._d.device
+            p = pts.reshape(-1, self.dim).to(dev).contiguous()
+            n = p.shape[0]
+            lo, res, dims, f32 = self._geom()
+            data = self._data_u8()
+            per_point = None
+            scalar = 0.0
+            if torch.is_tensor(value) and value.numel() > 1:
+                per_point = value.reshape(-1).to(device=dev, dtype=self._d.dtype).contiguous()
+                if per_point.numel() != n:
+                    raise ValueError(f"{per_point.numel()} values for {n} points")
+                per_point = per_point.view(torch.uint8) if per_point.dtype == torch.bool else per_point
+            else:
+                scalar = float(value.item() if torch.is_tensor(value) else value)
+            with torch.cuda.device(dev):
+                nat.check(nat.lib().pvb_voxel_scatter(self.dim, lo, res, dims, f32, nat.ptr(p), n,
+                                                      4 if data.dtype == torch.float32 else 1, nat.ptr(per_point),
+                                                      scalar, nat.ptr(data), nat.stream_ptr(dev)), "pvb_voxel_scatter")
+            return
         p = pts.reshape(-1, pts.shape[-1]).to(self.device)
         idx = self.ensure_index_key(p)
         upper = torch.tensor(self.shape, device=self.device)
@@ -164,7 +257,7 @@ class VoxelGrid(Voxels):
 
     def get_known_pos_and_values(self):
         flat = self.voxels.raw_data
-        filled = (flat != self.invalid_val).nonzero().reshape(-1)
+        filled = nonempty_indices(flat, self.invalid_val)           # ordered compaction kernel on CUDA grids
         cells = torch.stack(torch.unravel_index(filled, tuple(self.voxels.shape)), dim=-1)
         return self.voxels.ensure_value_key(cells), flat[filled]
 
