@@ -67,7 +67,8 @@ static int sm_count() {
 // Opt-in to > 48 KB of dynamic shared memory for `kernel`, once per (kernel, device).  `slot` is a small per-kernel
 // id; returns false when the runtime refuses.
 enum { kSlotMesh = 0, kSlotGridTma, kSlotCfgMajor, kSlotCfgMajorMulti, kSlotChamfer, kSlotRobot, kSlotRobotMulti,
-       kSlotRobotMc, kSlotRobotWide, kSlotRobotWideMulti, kSlotRobotWideMc, kSlotCount };
+       kSlotRobotMc, kSlotRobotWide, kSlotRobotWideMulti, kSlotRobotWideMc, kSlotSerial, kSlotSerialMulti, kSlotSerialMc,
+       kSlotCount };
 template <typename K>
 static bool ensure_smem(K kernel, int slot, int bytes) {
     static unsigned char done[kSlotCount][kMaxDevices] = {{0}};
@@ -1008,7 +1009,7 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
 #define PVB_ROBOT_PTS 4       // points per thread (4 or 2)
 #endif
 #ifndef PVB_ROBOT_MINB
-#define PVB_ROBOT_MINB 4      // resident CTAs per SM the <= 8-link instantiation is compiled for (register budget)
+#define PVB_ROBOT_MINB 3      // resident CTAs per SM the <= 8-link instantiation is compiled for: 80 registers, no spills (0.75 ms on C4 against 0.82 ms at 64 registers with spills)
 #endif
 #ifndef PVB_ROBOT_UNROLL
 #define PVB_ROBOT_UNROLL 0    // 1: fully unrolled link loop (descriptor fields become immediates, but the 8 x kRbPts inlined
@@ -1310,6 +1311,220 @@ robot_query_kernel(const __grid_constant__ RobotPack<MAXS> pk, int n_sdf, const 
             }
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// RobotSDF kernel, third generation: point-serial, nearest-sphere-first.
+// What the profiles of robot_query_kernel said (profiles/r02/c4_robot_r_p4m3.ncu.json): 454 M warp-instructions for
+// 2e7 pairs, of which 62 % in link visits that run for 5.3 of the 8 links per (point, 32 configurations) although a lane
+// needs 3.1 -- a fixed visiting order lets the running minimum tighten slowly, and "any lane needs it" makes the whole
+// warp pay; 17 % in the bounding-sphere tests of all 8 links x 4 points; L1 wavefronts at 51 % (16-byte stores to 32
+// different rows per instruction); 80 registers, 33 % warps active, long-scoreboard (gather latency) the top stall.
+//   * one point at a time per warp (lanes = 32 configurations), so the state of a point is 8 registers, not 32;
+//   * the lane's 8 bounding spheres live in REGISTERS for the whole kernel (they were 4 LDS wavefronts per link and
+//     point); per point one pass turns them into lower bounds lb_s <= value_s, kept in 8 registers;
+//   * the link with the smallest bound (lane 0's, shuffled: neighbouring configurations agree) is visited FIRST, so
+//     the running minimum is tight at once and `lb_s > best` (one compare) rejects most other links for most lanes;
+//     ties keep torch.argmin's first-index rule explicitly, so the order never changes a result;
+//   * results of 8 consecutive points are parked in a per-WARP staging tile and leave as whole sectors (32 B of
+//     values + 96 B of gradients per configuration row), one 16-byte store per lane and destination -- local
+//     buffer, peer buffers or multicast -- with __syncwarp only: no block barrier anywhere in the loop.
+// Pruning stays exact (bounds are conservative), arithmetic of a visit is unchanged: bit-identical to the other kernels.
+constexpr int kRsWarps = 8;
+constexpr int kRsChunk = 8;                       // consecutive points per warp between two flushes
+constexpr int kRsMaxS = 8;
+constexpr int kRsValStride = kRsChunk + 1;        // 9: conflict-free STS.32 across lanes
+constexpr int kRsGradStride = 3 * kRsChunk + 1;   // 25
+
+#ifndef PVB_RS_SPH_SMEM
+#define PVB_RS_SPH_SMEM 1     // 1: bounding spheres read from shared memory per point (4 LDS wavefronts per link);
+#endif                        // 0: kept in 32 registers per thread (no LDS, but 80+ registers: 3 CTAs per SM)
+#ifndef PVB_RS_MINB
+#define PVB_RS_MINB 4
+#endif
+
+struct __align__(16) RsSmem {
+    float4 xf[kRbCfg][3 * kRsMaxS + 1];
+    float4 sph[kRbCfg][kRsMaxS + 1];
+    float sv[kRsWarps][kRbCfg][kRsValStride];
+    float sg[kRsWarps][kRbCfg][kRsGradStride];
+};
+
+template <int kDest>
+__global__ void __launch_bounds__(kRbCfg * kRsWarps, PVB_RS_MINB)
+robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, const float *__restrict__ xforms,
+                    int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, int n_pts, int vec,
+                    float *__restrict__ out_val, float *__restrict__ out_grad, int *__restrict__ out_which,
+                    const __grid_constant__ OutTargets tg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.y * kRbCfg;                       // first configuration (relative to cfg_begin)
+    const int ncfg = min(kRbCfg, cfg_count - c0);
+    const bool lane_on = lane < ncfg;
+    // ---- stage the transforms of this configuration tile ----
+    for (int item = threadIdx.x; item < kRbCfg * n_sdf; item += blockDim.x) {
+        const int ci = item % kRbCfg, si = item / kRbCfg;
+        float4 r0 = make_float4(1.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 1.f, 0.f, 0.f),
+               r2 = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (ci < ncfg) {
+            const float4 *row = reinterpret_cast<const float4 *>(xforms + ((size_t)si * n_cfg + cfg_begin + c0 + ci) * 16);
+            r0 = __ldg(row); r1 = __ldg(row + 1); r2 = __ldg(row + 2);
+        }
+        sm.xf[ci][3 * si] = r0; sm.xf[ci][3 * si + 1] = r1; sm.xf[ci][3 * si + 2] = r2;
+    }
+    __syncthreads();
+    // ---- this lane's bounding spheres (object frame): registers for the whole kernel, or shared memory ----
+#if !PVB_RS_SPH_SMEM
+    float4 sph[kRsMaxS];
+#endif
+#pragma unroll
+    for (int si = 0; si < kRsMaxS; ++si) {
+#if PVB_RS_SPH_SMEM
+        if (warp == 0) sm.sph[lane][si] = make_float4(0.f, 0.f, 0.f, PVB_INF);
+        if (si < n_sdf && warp == 0) {
+#else
+        sph[si] = make_float4(0.f, 0.f, 0.f, PVB_INF);
+        if (si < n_sdf) {
+#endif
+            const pvb_sdf_desc &d = pk.d[si];
+            const float4 r0 = sm.xf[lane][3 * si], r1 = sm.xf[lane][3 * si + 1], r2 = sm.xf[lane][3 * si + 2];
+            // sphere around the link AABB, centre carried to the object frame: c_obj = R^T (c_link - t)
+            const f3 cl = mk3(0.5f * (d.bb_min[0] + d.bb_max[0]), 0.5f * (d.bb_min[1] + d.bb_max[1]),
+                              0.5f * (d.bb_min[2] + d.bb_max[2]));
+            const f3 hl = mk3(0.5f * (d.bb_max[0] - d.bb_min[0]), 0.5f * (d.bb_max[1] - d.bb_min[1]),
+                              0.5f * (d.bb_max[2] - d.bb_min[2]));
+            const f3 u = mk3(cl.x - r0.w, cl.y - r1.w, cl.z - r2.w);
+            const f3 co = mk3(r0.x * u.x + r1.x * u.y + r2.x * u.z, r0.y * u.x + r1.y * u.y + r2.y * u.z,
+                              r0.z * u.x + r1.z * u.y + r2.z * u.z);
+            float rad = sqrtf(hl.x * hl.x + hl.y * hl.y + hl.z * hl.z) * 1.0001f + 1e-6f;
+            // the bound needs an isometry: |R R^T - I| must vanish, otherwise this (cfg, link) is never rejected by it
+            const float e00 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z - 1.f, e11 = r1.x * r1.x + r1.y * r1.y + r1.z * r1.z - 1.f,
+                        e22 = r2.x * r2.x + r2.y * r2.y + r2.z * r2.z - 1.f;
+            const float e01 = r0.x * r1.x + r0.y * r1.y + r0.z * r1.z, e02 = r0.x * r2.x + r0.y * r2.y + r0.z * r2.z,
+                        e12 = r1.x * r2.x + r1.y * r2.y + r1.z * r2.z;
+            const float dev = fmaxf(fmaxf(fmaxf(fabsf(e00), fabsf(e11)), fmaxf(fabsf(e22), fabsf(e01))),
+                                    fmaxf(fabsf(e02), fabsf(e12)));
+            const bool ok = (d.flags & PVB_GRID_PRUNE_OK) && dev < 1e-5f;
+#if PVB_RS_SPH_SMEM
+            sm.sph[lane][si] = make_float4(co.x, co.y, co.z, ok ? rad + d.prune_margin : PVB_INF);
+#else
+            sph[si] = make_float4(co.x, co.y, co.z, ok ? rad + d.prune_margin : PVB_INF);
+#endif
+        }
+    }
+#if PVB_RS_SPH_SMEM
+    __syncthreads();
+#endif
+    float *sv = &sm.sv[warp][0][0];
+    float *sg = &sm.sg[warp][0][0];
+    const int n_chunks = (n_pts + kRsChunk - 1) / kRsChunk;
+    for (int chunk = blockIdx.x * kRsWarps + warp; chunk < n_chunks; chunk += gridDim.x * kRsWarps) {
+        const int pt_base = chunk * kRsChunk;
+        const int n_here = min(kRsChunk, n_pts - pt_base);
+#pragma unroll 1
+        for (int k = 0; k < n_here; ++k) {
+            const f3 p = load_point(pts, pt_base + k);            // uniform across the warp
+            // ---- lower bounds of every link's value from its bounding sphere: value_s >= |p - c_s| - radius_s.
+            // 0.9998 absorbs the 1e-5 non-rigidity tolerated above, 0.999999 the approximate square root;
+            // radius = inf (bound not valid) gives -inf: never rejected.  d2 = 0 gives NaN: never rejected either.
+            float lb[kRsMaxS];
+            float lb_min = PVB_INF;
+            int pred = 0;
+#pragma unroll
+            for (int si = 0; si < kRsMaxS; ++si) {
+#if PVB_RS_SPH_SMEM
+                const float4 sp = sm.sph[lane][si];
+#else
+                const float4 sp = sph[si];
+#endif
+                const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
+                const float d2 = (dx * dx + dy * dy + dz * dz) * 0.9998f;
+                lb[si] = fmaf(d2 * rsqrtf(d2), 0.999999f, -sp.w);
+                if (si < n_sdf && lb[si] < lb_min) { lb_min = lb[si]; pred = si; }
+            }
+            pred = __shfl_sync(0xffffffffu, pred, 0);             // one order for the warp: lane 0's nearest sphere
+            float best = PVB_INF;
+            f3 bg = mk3(0.f, 0.f, 0.f);
+            int bs = -1;
+            // one link: transform, AABB bound against the running minimum, nearest-voxel lookup, running argmin
+            auto visit = [&](const pvb_sdf_desc &d, const int si) {
+                const float4 r0 = sm.xf[lane][3 * si], r1 = sm.xf[lane][3 * si + 1], r2 = sm.xf[lane][3 * si + 2];
+                const f3 q = composed_xform(r0, r1, r2, p);
+                if ((d.flags & PVB_GRID_PRUNE_OK) && bs >= 0) {
+                    const float thr = best + d.prune_margin;
+                    if (thr < 0.f || composed_aabb_lb2(d, q) > thr * thr) return;
+                }
+                const float4 o = robot_lookup(d, q);
+                if (bs < 0 || o.x < best || (o.x == best && si < bs)) {
+                    best = o.x; bg = mk3(o.y, o.z, o.w); bs = si;
+                }
+            };
+            if (lane_on) visit(pk.d[pred], pred);
+#pragma unroll
+            for (int si = 0; si < kRsMaxS; ++si) {
+                if (si < n_sdf && si != pred) {
+                    // reject when the sphere bound already exceeds the running minimum (exact: lb <= value)
+                    if (lane_on && !(lb[si] > best)) visit(pk.d[si], si);
+                }
+            }
+            const int sb = max(bs, 0);
+            const f3 go = composed_rotate_back(sm.xf[lane][3 * sb], sm.xf[lane][3 * sb + 1], sm.xf[lane][3 * sb + 2], bg);
+            sv[lane * kRsValStride + k] = best;
+            sg[lane * kRsGradStride + 3 * k] = go.x;
+            sg[lane * kRsGradStride + 3 * k + 1] = go.y;
+            sg[lane * kRsGradStride + 3 * k + 2] = go.z;
+            if (out_which && lane_on) out_which[(size_t)(c0 + lane) * n_pts + pt_base + k] = bs;
+        }
+        __syncwarp();
+        // ---- flush: 32 configuration rows x (8 values = one 32-byte sector, 24 gradient floats = three) ----
+        if (vec && n_here == kRsChunk) {
+            // values: 64 chunks of 16 B, gradients: 192 -- lane i takes chunks i, i + 32, ...
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                const bool is_val = j < 2;
+                const int row = is_val ? c >> 1 : (c - 64) / 6;
+                const int part = is_val ? c & 1 : (c - 64) % 6;
+                if (row < ncfg) {
+                    const float *src = is_val ? sv + row * kRsValStride + 4 * part : sg + row * kRsGradStride + 4 * part;
+                    const float4 v4 = make_float4(src[0], src[1], src[2], src[3]);
+                    const size_t o_row = (size_t)(c0 + row) * n_pts + pt_base;
+                    const size_t off = is_val ? o_row + 4 * part : 3 * o_row + 4 * part;
+                    if constexpr (kDest == 0) {
+                        __stcs(reinterpret_cast<float4 *>((is_val ? out_val : out_grad) + off), v4);
+                    } else if constexpr (kDest == 1) {
+                        for (int t = 0; t < tg.n; ++t)
+                            __stcs(reinterpret_cast<float4 *>((is_val ? tg.val[t] : tg.grad[t]) + off), v4);
+                    } else {
+                        st_mc_v4((is_val ? tg.val[0] : tg.grad[0]) + off, v4);
+                    }
+                }
+            }
+        } else if (lane_on) {
+            for (int k = 0; k < n_here; ++k) {
+                const float v = sv[lane * kRsValStride + k];
+                const float gx = sg[lane * kRsGradStride + 3 * k], gy = sg[lane * kRsGradStride + 3 * k + 1],
+                            gz = sg[lane * kRsGradStride + 3 * k + 2];
+                const size_t o_i = (size_t)(c0 + lane) * n_pts + pt_base + k;
+                if constexpr (kDest == 0) {
+                    __stcs(out_val + o_i, v);
+                    __stcs(out_grad + 3 * o_i, gx); __stcs(out_grad + 3 * o_i + 1, gy); __stcs(out_grad + 3 * o_i + 2, gz);
+                } else if constexpr (kDest == 1) {
+                    for (int t = 0; t < tg.n; ++t) {
+                        __stcs(tg.val[t] + o_i, v);
+                        __stcs(tg.grad[t] + 3 * o_i, gx); __stcs(tg.grad[t] + 3 * o_i + 1, gy);
+                        __stcs(tg.grad[t] + 3 * o_i + 2, gz);
+                    }
+                } else {
+                    st_mc_f32(tg.val[0] + o_i, v);
+                    st_mc_f32(tg.grad[0] + 3 * o_i, gx); st_mc_f32(tg.grad[0] + 3 * o_i + 1, gy);
+                    st_mc_f32(tg.grad[0] + 3 * o_i + 2, gz);
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -1994,6 +2209,47 @@ static int launch_robot(const pvb_sdf_desc *descs, int n_sdf, const float *xform
     return PVB_OK;
 }
 
+// Launch robot_serial_kernel (<= 8 GRID sub-SDFs with the bounding-box rule).
+static int launch_robot_serial(const pvb_sdf_desc *descs, int n_sdf, const float *xforms, int n_cfg, int cfg_begin,
+                               int cfg_count, const float *pts, long long n_pts, int vec, float *out_val,
+                               float *out_grad, int *out_which, const OutTargets *tg, cudaStream_t stream) {
+    RobotPack<kRsMaxS> pack;
+    memset(&pack, 0, sizeof(pack));
+    for (int si = 0; si < n_sdf; ++si) { pack.d[si] = descs[si]; pack.orig[si] = si; }
+    const int kind = !tg ? 0 : (tg->mc ? 2 : 1);
+    auto k0 = robot_serial_kernel<0>;
+    auto k1 = robot_serial_kernel<1>;
+    auto k2 = robot_serial_kernel<2>;
+    const int smem = (int)sizeof(RsSmem);
+    if (!ensure_smem(k0, kSlotSerial, smem) || !ensure_smem(k1, kSlotSerial + 1, smem) ||
+        !ensure_smem(k2, kSlotSerial + 2, smem)) {
+        pvb_set_error("pvb_composed_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+        return PVB_ERR_CUDA;
+    }
+    const int gy = (cfg_count + kRbCfg - 1) / kRbCfg;
+    const long long n_chunks = (n_pts + kRsChunk - 1) / kRsChunk;
+    static const int waves = [] { const char *e = getenv("PVB_ROBOT_WAVES"); return e ? atoi(e) : 8; }();
+    long long gx = ((long long)sm_count() * 4 * waves + gy - 1) / gy;
+    const long long gx_max = (n_chunks + kRsWarps - 1) / kRsWarps;
+    if (gx > gx_max) gx = gx_max;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    const OutTargets none{};
+    timing_mark(0, stream);
+    if (kind == 0)
+        k0<<<grid, kRbCfg * kRsWarps, smem, stream>>>(pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, (int)n_pts,
+                                                      vec, out_val, out_grad, out_which, none);
+    else if (kind == 1)
+        k1<<<grid, kRbCfg * kRsWarps, smem, stream>>>(pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, (int)n_pts,
+                                                      vec, nullptr, nullptr, out_which, *tg);
+    else
+        k2<<<grid, kRbCfg * kRsWarps, smem, stream>>>(pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, (int)n_pts,
+                                                      vec, nullptr, nullptr, out_which, *tg);
+    timing_mark(1, stream);
+    PVB_CHECK_LAUNCH("pvb_composed_query(robot-serial)");
+    return PVB_OK;
+}
+
 // tg == nullptr: one destination (out_val / out_grad); otherwise the kMulti instantiations store to every target
 static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t needs_mesh, const float *xforms,
                              int32_t n_cfg, int32_t cfg_begin, int32_t cfg_count, const float *pts, int64_t n_pts,
@@ -2042,7 +2298,7 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
     // sectors, which is what the NVLink-bound re-assembly needs; idle lanes cost less than partial-sector packets
     const bool cm_filled = (cfg_count >= 16 && (double)cfg_count >= 0.85 * (double)(cm_tiles * kCmCfg)) ||
                            (tg && tg->vec && cfg_count >= 8);
-    static const int robot_kernel = [] { const char *e = getenv("PVB_ROBOT_KERNEL"); return e ? atoi(e) : 1; }();
+    static const int robot_kernel = [] { const char *e = getenv("PVB_ROBOT_KERNEL"); return e ? atoi(e) : 2; }();
     static const double robot_fill = [] { const char *e = getenv("PVB_ROBOT_MIN_FILL"); return e ? atof(e) : 0.85; }();
     bool all_grid = !needs_mesh && n_sdf <= 16 && n_pts < (1ll << 31);
     for (int i = 0; i < n_sdf && all_grid; ++i)
@@ -2051,6 +2307,12 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
                            (tg && tg->vec && cfg_count >= 8) || (tg && tg->mc);
     if (robot_kernel && cfg_major && all_grid && rb_filled) {
         const int vec_rows = (tg ? tg->vec : (out_aligned && (n_pts % 4 == 0))) && aligned16(pts);
+        // PVB_ROBOT_KERNEL: 2 (default) = point-serial nearest-sphere-first kernel for <= 8 links, 1 = the
+        // 4-points-per-thread kernel, 0 = round 1's configuration-major kernel
+        if (robot_kernel >= 2 && n_sdf <= kRsMaxS)
+            return launch_robot_serial(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts,
+                                       (tg ? tg->vec : (out_aligned && (n_pts % 4 == 0))), out_val, out_grad, out_which,
+                                       tg, s);
         return n_sdf <= 8 ? launch_robot<8, true>(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts, vec_rows,
                                                   out_val, out_grad, out_which, tg, s)
                           : launch_robot<16, false>(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts,
