@@ -1337,9 +1337,9 @@ constexpr int kRsMaxS = 8;
 constexpr int kRsValStride = kRsChunk + 1;        // 9: conflict-free STS.32 across lanes
 constexpr int kRsGradStride = 3 * kRsChunk + 1;   // 25
 
-#ifndef PVB_RS_SPH_SMEM
-#define PVB_RS_SPH_SMEM 1     // 1: bounding spheres read from shared memory per point (4 LDS wavefronts per link);
-#endif                        // 0: kept in 32 registers per thread (no LDS, but 80+ registers: 3 CTAs per SM)
+// (The lane's 8 bounding spheres kept in 32 registers instead of shared memory -- no LDS in the bound pass, but 80
+// registers / 3 CTAs per SM -- measured 0.70 ms against 0.56 ms for the shared-memory form on C4; 48 registers / 5 CTAs
+// with spills 0.70 ms; 80 registers without spills 0.60 ms: profiles/r02/tune_c4_serial_variants.jsonl.)
 #ifndef PVB_RS_MINB
 #define PVB_RS_MINB 4
 #endif
@@ -1347,9 +1347,36 @@ constexpr int kRsGradStride = 3 * kRsChunk + 1;   // 25
 struct __align__(16) RsSmem {
     float4 xf[kRbCfg][3 * kRsMaxS + 1];
     float4 sph[kRbCfg][kRsMaxS + 1];
+    // per-warp staging, LC rows x (8 * 32/LC values + 1) resp. (24 * 32/LC gradient floats + 1): at most 32 x 9 / 32 x 25
     float sv[kRsWarps][kRbCfg][kRsValStride];
     float sg[kRsWarps][kRbCfg][kRsGradStride];
 };
+
+__device__ __forceinline__ float rsqrt_approx(float x) {      // one MUFU.RSQ, no denormal fix-up (callers keep x >= 1e-20)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Configuration tiles.  The first cfg_count / 32 tiles hold 32 configurations each (lanes = configurations, one point
+// per warp step).  The remainder R = cfg_count % 32 is split by its binary digits into FULL tiles of 16 / 8 / 4 / 2 / 1
+// configurations, in which the 32 lanes are 32 / LC point groups x LC configurations: no lane ever idles because the
+// configuration count is not a multiple of 32 (200 = 6 x 32 + 8 ran a seventh tile at 8 of 32 lanes: 11 % of the time;
+// the 25-configuration slab of an 8-GPU split ran at 25 of 32).
+__device__ __forceinline__ void rs_tile(int cfg_count, int t, int &c0, int &lc_log2) {
+    const int n_full = cfg_count >> 5;
+    if (t < n_full) { c0 = t << 5; lc_log2 = 5; return; }
+    int rem = cfg_count & 31, idx = t - n_full;
+    c0 = n_full << 5;
+    lc_log2 = 0;
+    for (int b = 4; b >= 0; --b) {
+        if (rem & (1 << b)) {
+            if (idx == 0) { lc_log2 = b; return; }
+            --idx;
+            c0 += 1 << b;
+        }
+    }
+}
 
 template <int kDest>
 __global__ void __launch_bounds__(kRbCfg * kRsWarps, PVB_RS_MINB)
@@ -1360,45 +1387,37 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = blockIdx.y * kRbCfg;                       // first configuration (relative to cfg_begin)
-    const int ncfg = min(kRbCfg, cfg_count - c0);
-    const bool lane_on = lane < ncfg;
+    int c0, lc_log2;
+    rs_tile(cfg_count, blockIdx.y, c0, lc_log2);              // first configuration (relative to cfg_begin), log2(lanes per point)
+    const int LC = 1 << lc_log2;                              // configurations of this tile = lanes per point group
+    const int sub_log2 = 5 - lc_log2, SUB = 1 << sub_log2;    // point groups per warp
+    const int cl = lane & (LC - 1), sub = lane >> lc_log2;    // this lane's configuration / point group
+    const int pts_per_step = kRsChunk * SUB;                  // points a warp finishes between two flushes
+    const int n_chunks = (n_pts + pts_per_step - 1) / pts_per_step;
+    if ((int)(blockIdx.x * kRsWarps) >= n_chunks) return;     // small tiles need fewer blocks (uniform per block)
     // ---- stage the transforms of this configuration tile ----
-    for (int item = threadIdx.x; item < kRbCfg * n_sdf; item += blockDim.x) {
-        const int ci = item % kRbCfg, si = item / kRbCfg;
-        float4 r0 = make_float4(1.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 1.f, 0.f, 0.f),
-               r2 = make_float4(0.f, 0.f, 1.f, 0.f);
-        if (ci < ncfg) {
-            const float4 *row = reinterpret_cast<const float4 *>(xforms + ((size_t)si * n_cfg + cfg_begin + c0 + ci) * 16);
-            r0 = __ldg(row); r1 = __ldg(row + 1); r2 = __ldg(row + 2);
-        }
-        sm.xf[ci][3 * si] = r0; sm.xf[ci][3 * si + 1] = r1; sm.xf[ci][3 * si + 2] = r2;
+    for (int item = threadIdx.x; item < LC * n_sdf; item += blockDim.x) {
+        const int ci = item & (LC - 1), si = item >> lc_log2;
+        const float4 *row = reinterpret_cast<const float4 *>(xforms + ((size_t)si * n_cfg + cfg_begin + c0 + ci) * 16);
+        sm.xf[ci][3 * si] = __ldg(row); sm.xf[ci][3 * si + 1] = __ldg(row + 1); sm.xf[ci][3 * si + 2] = __ldg(row + 2);
     }
     __syncthreads();
-    // ---- this lane's bounding spheres (object frame): registers for the whole kernel, or shared memory ----
-#if !PVB_RS_SPH_SMEM
-    float4 sph[kRsMaxS];
-#endif
-#pragma unroll
-    for (int si = 0; si < kRsMaxS; ++si) {
-#if PVB_RS_SPH_SMEM
-        if (warp == 0) sm.sph[lane][si] = make_float4(0.f, 0.f, 0.f, PVB_INF);
-        if (si < n_sdf && warp == 0) {
-#else
-        sph[si] = make_float4(0.f, 0.f, 0.f, PVB_INF);
+    // ---- bounding spheres (object frame) of every (configuration, link) of the tile ----
+    for (int item = threadIdx.x; item < LC * kRsMaxS; item += blockDim.x) {
+        const int ci = item & (LC - 1), si = item >> lc_log2;
+        float4 sp = make_float4(0.f, 0.f, 0.f, PVB_INF);
         if (si < n_sdf) {
-#endif
             const pvb_sdf_desc &d = pk.d[si];
-            const float4 r0 = sm.xf[lane][3 * si], r1 = sm.xf[lane][3 * si + 1], r2 = sm.xf[lane][3 * si + 2];
+            const float4 r0 = sm.xf[ci][3 * si], r1 = sm.xf[ci][3 * si + 1], r2 = sm.xf[ci][3 * si + 2];
             // sphere around the link AABB, centre carried to the object frame: c_obj = R^T (c_link - t)
-            const f3 cl = mk3(0.5f * (d.bb_min[0] + d.bb_max[0]), 0.5f * (d.bb_min[1] + d.bb_max[1]),
-                              0.5f * (d.bb_min[2] + d.bb_max[2]));
+            const f3 cen = mk3(0.5f * (d.bb_min[0] + d.bb_max[0]), 0.5f * (d.bb_min[1] + d.bb_max[1]),
+                               0.5f * (d.bb_min[2] + d.bb_max[2]));
             const f3 hl = mk3(0.5f * (d.bb_max[0] - d.bb_min[0]), 0.5f * (d.bb_max[1] - d.bb_min[1]),
                               0.5f * (d.bb_max[2] - d.bb_min[2]));
-            const f3 u = mk3(cl.x - r0.w, cl.y - r1.w, cl.z - r2.w);
+            const f3 u = mk3(cen.x - r0.w, cen.y - r1.w, cen.z - r2.w);
             const f3 co = mk3(r0.x * u.x + r1.x * u.y + r2.x * u.z, r0.y * u.x + r1.y * u.y + r2.y * u.z,
                               r0.z * u.x + r1.z * u.y + r2.z * u.z);
-            float rad = sqrtf(hl.x * hl.x + hl.y * hl.y + hl.z * hl.z) * 1.0001f + 1e-6f;
+            const float rad = sqrtf(hl.x * hl.x + hl.y * hl.y + hl.z * hl.z) * 1.0001f + 1e-6f;
             // the bound needs an isometry: |R R^T - I| must vanish, otherwise this (cfg, link) is never rejected by it
             const float e00 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z - 1.f, e11 = r1.x * r1.x + r1.y * r1.y + r1.z * r1.z - 1.f,
                         e22 = r2.x * r2.x + r2.y * r2.y + r2.z * r2.z - 1.f;
@@ -1407,50 +1426,46 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
             const float dev = fmaxf(fmaxf(fmaxf(fabsf(e00), fabsf(e11)), fmaxf(fabsf(e22), fabsf(e01))),
                                     fmaxf(fabsf(e02), fabsf(e12)));
             const bool ok = (d.flags & PVB_GRID_PRUNE_OK) && dev < 1e-5f;
-#if PVB_RS_SPH_SMEM
-            sm.sph[lane][si] = make_float4(co.x, co.y, co.z, ok ? rad + d.prune_margin : PVB_INF);
-#else
-            sph[si] = make_float4(co.x, co.y, co.z, ok ? rad + d.prune_margin : PVB_INF);
-#endif
+            sp = make_float4(co.x, co.y, co.z, ok ? rad + d.prune_margin : PVB_INF);
         }
+        sm.sph[ci][si] = sp;
     }
-#if PVB_RS_SPH_SMEM
     __syncthreads();
-#endif
-    float *sv = &sm.sv[warp][0][0];
+    float *sv = &sm.sv[warp][0][0];                 // this warp's staging: LC rows x (8 SUB values | 24 SUB gradient floats)
     float *sg = &sm.sg[warp][0][0];
-    const int n_chunks = (n_pts + kRsChunk - 1) / kRsChunk;
+    const int vstride = pts_per_step + 1, gstride = 3 * pts_per_step + 1;     // odd: conflict-free STS.32 across lanes
     for (int chunk = blockIdx.x * kRsWarps + warp; chunk < n_chunks; chunk += gridDim.x * kRsWarps) {
-        const int pt_base = chunk * kRsChunk;
-        const int n_here = min(kRsChunk, n_pts - pt_base);
+        const int pt_base = chunk * pts_per_step;
+        const bool full = pt_base + pts_per_step <= n_pts;
 #pragma unroll 1
-        for (int k = 0; k < n_here; ++k) {
-            const f3 p = load_point(pts, pt_base + k);            // uniform across the warp
+        for (int k = 0; k < kRsChunk; ++k) {
+            const int pt = pt_base + sub * kRsChunk + k;
+            const bool on = pt < n_pts;
+            if (!full && !__any_sync(0xffffffffu, on)) break;
+            const f3 p = on ? load_point(pts, pt) : mk3(0.f, 0.f, 0.f);     // the same for the LC lanes of a point group
             // ---- lower bounds of every link's value from its bounding sphere: value_s >= |p - c_s| - radius_s.
-            // 0.9998 absorbs the 1e-5 non-rigidity tolerated above, 0.999999 the approximate square root;
-            // radius = inf (bound not valid) gives -inf: never rejected.  d2 = 0 gives NaN: never rejected either.
+            // 0.9998 absorbs the 1e-5 non-rigidity tolerated above, 0.999999 the approximate reciprocal square root
+            // (2 ulp); + 1e-20 keeps its argument a normal number (and raises the bound by < 1e-10, inside the 1e-5
+            // slack of the radius).  radius = inf (bound not valid) gives -inf: never rejected.
             float lb[kRsMaxS];
             float lb_min = PVB_INF;
             int pred = 0;
 #pragma unroll
             for (int si = 0; si < kRsMaxS; ++si) {
-#if PVB_RS_SPH_SMEM
-                const float4 sp = sm.sph[lane][si];
-#else
-                const float4 sp = sph[si];
-#endif
+                const float4 sp = sm.sph[cl][si];
                 const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
-                const float d2 = (dx * dx + dy * dy + dz * dz) * 0.9998f;
-                lb[si] = fmaf(d2 * rsqrtf(d2), 0.999999f, -sp.w);
+                const float d2 = fmaf(dx * dx + dy * dy + dz * dz, 0.9998f, 1e-20f);
+                lb[si] = fmaf(d2 * rsqrt_approx(d2), 0.999999f, -sp.w);
                 if (si < n_sdf && lb[si] < lb_min) { lb_min = lb[si]; pred = si; }
             }
-            pred = __shfl_sync(0xffffffffu, pred, 0);             // one order for the warp: lane 0's nearest sphere
+            // one visiting order per point group: its first lane's nearest sphere (neighbouring configurations agree)
+            pred = __shfl_sync(0xffffffffu, pred, sub << lc_log2);
             float best = PVB_INF;
             f3 bg = mk3(0.f, 0.f, 0.f);
             int bs = -1;
             // one link: transform, AABB bound against the running minimum, nearest-voxel lookup, running argmin
             auto visit = [&](const pvb_sdf_desc &d, const int si) {
-                const float4 r0 = sm.xf[lane][3 * si], r1 = sm.xf[lane][3 * si + 1], r2 = sm.xf[lane][3 * si + 2];
+                const float4 r0 = sm.xf[cl][3 * si], r1 = sm.xf[cl][3 * si + 1], r2 = sm.xf[cl][3 * si + 2];
                 const f3 q = composed_xform(r0, r1, r2, p);
                 if ((d.flags & PVB_GRID_PRUNE_OK) && bs >= 0) {
                     const float thr = best + d.prune_margin;
@@ -1461,53 +1476,57 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
                     best = o.x; bg = mk3(o.y, o.z, o.w); bs = si;
                 }
             };
-            if (lane_on) visit(pk.d[pred], pred);
+            if (on) visit(pk.d[pred], pred);
 #pragma unroll
             for (int si = 0; si < kRsMaxS; ++si) {
-                if (si < n_sdf && si != pred) {
+                if (si < n_sdf) {
                     // reject when the sphere bound already exceeds the running minimum (exact: lb <= value)
-                    if (lane_on && !(lb[si] > best)) visit(pk.d[si], si);
+                    if (on && si != pred && !(lb[si] > best)) visit(pk.d[si], si);
                 }
             }
             const int sb = max(bs, 0);
-            const f3 go = composed_rotate_back(sm.xf[lane][3 * sb], sm.xf[lane][3 * sb + 1], sm.xf[lane][3 * sb + 2], bg);
-            sv[lane * kRsValStride + k] = best;
-            sg[lane * kRsGradStride + 3 * k] = go.x;
-            sg[lane * kRsGradStride + 3 * k + 1] = go.y;
-            sg[lane * kRsGradStride + 3 * k + 2] = go.z;
-            if (out_which && lane_on) out_which[(size_t)(c0 + lane) * n_pts + pt_base + k] = bs;
+            const f3 go = composed_rotate_back(sm.xf[cl][3 * sb], sm.xf[cl][3 * sb + 1], sm.xf[cl][3 * sb + 2], bg);
+            const int col = sub * kRsChunk + k;
+            sv[cl * vstride + col] = best;
+            sg[cl * gstride + 3 * col] = go.x;
+            sg[cl * gstride + 3 * col + 1] = go.y;
+            sg[cl * gstride + 3 * col + 2] = go.z;
+            if (out_which && on) out_which[(size_t)(c0 + cl) * n_pts + pt] = bs;
         }
         __syncwarp();
-        // ---- flush: 32 configuration rows x (8 values = one 32-byte sector, 24 gradient floats = three) ----
-        if (vec && n_here == kRsChunk) {
-            // values: 64 chunks of 16 B, gradients: 192 -- lane i takes chunks i, i + 32, ...
+        // ---- flush: LC configuration rows x (8 SUB values | 24 SUB gradient floats), all whole 32-byte sectors ----
+        if (vec && full) {
+            // 256 chunks of 16 B per warp step: the first 64 are values, the other 192 gradients; lane i takes i, i + 32, ...
+            const int vper = 2 << sub_log2, gper = 6 << sub_log2;        // chunks per row
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = lane + 32 * j;
                 const bool is_val = j < 2;
-                const int row = is_val ? c >> 1 : (c - 64) / 6;
-                const int part = is_val ? c & 1 : (c - 64) % 6;
-                if (row < ncfg) {
-                    const float *src = is_val ? sv + row * kRsValStride + 4 * part : sg + row * kRsGradStride + 4 * part;
-                    const float4 v4 = make_float4(src[0], src[1], src[2], src[3]);
-                    const size_t o_row = (size_t)(c0 + row) * n_pts + pt_base;
-                    const size_t off = is_val ? o_row + 4 * part : 3 * o_row + 4 * part;
-                    if constexpr (kDest == 0) {
-                        __stcs(reinterpret_cast<float4 *>((is_val ? out_val : out_grad) + off), v4);
-                    } else if constexpr (kDest == 1) {
-                        for (int t = 0; t < tg.n; ++t)
-                            __stcs(reinterpret_cast<float4 *>((is_val ? tg.val[t] : tg.grad[t]) + off), v4);
-                    } else {
-                        st_mc_v4((is_val ? tg.val[0] : tg.grad[0]) + off, v4);
-                    }
+                const int g = is_val ? c : c - 64;
+                const int row = is_val ? g >> (1 + sub_log2) : (g >> sub_log2) / 6;
+                const int part = is_val ? g & (vper - 1) : g - row * gper;
+                const float *src = is_val ? sv + row * vstride + 4 * part : sg + row * gstride + 4 * part;
+                const float4 v4 = make_float4(src[0], src[1], src[2], src[3]);
+                const size_t o_row = (size_t)(c0 + row) * n_pts + pt_base;
+                const size_t off = is_val ? o_row + 4 * part : 3 * o_row + 4 * part;
+                if constexpr (kDest == 0) {
+                    __stcs(reinterpret_cast<float4 *>((is_val ? out_val : out_grad) + off), v4);
+                } else if constexpr (kDest == 1) {
+                    for (int t = 0; t < tg.n; ++t)
+                        __stcs(reinterpret_cast<float4 *>((is_val ? tg.val[t] : tg.grad[t]) + off), v4);
+                } else {
+                    st_mc_v4((is_val ? tg.val[0] : tg.grad[0]) + off, v4);
                 }
             }
-        } else if (lane_on) {
-            for (int k = 0; k < n_here; ++k) {
-                const float v = sv[lane * kRsValStride + k];
-                const float gx = sg[lane * kRsGradStride + 3 * k], gy = sg[lane * kRsGradStride + 3 * k + 1],
-                            gz = sg[lane * kRsGradStride + 3 * k + 2];
-                const size_t o_i = (size_t)(c0 + lane) * n_pts + pt_base + k;
+        } else {
+            for (int k = 0; k < kRsChunk; ++k) {
+                const int col = sub * kRsChunk + k;
+                const int pt = pt_base + col;
+                if (pt >= n_pts) break;
+                const float v = sv[cl * vstride + col];
+                const float gx = sg[cl * gstride + 3 * col], gy = sg[cl * gstride + 3 * col + 1],
+                            gz = sg[cl * gstride + 3 * col + 2];
+                const size_t o_i = (size_t)(c0 + cl) * n_pts + pt;
                 if constexpr (kDest == 0) {
                     __stcs(out_val + o_i, v);
                     __stcs(out_grad + 3 * o_i, gx); __stcs(out_grad + 3 * o_i + 1, gy); __stcs(out_grad + 3 * o_i + 2, gz);
@@ -2226,9 +2245,10 @@ static int launch_robot_serial(const pvb_sdf_desc *descs, int n_sdf, const float
         pvb_set_error("pvb_composed_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
         return PVB_ERR_CUDA;
     }
-    const int gy = (cfg_count + kRbCfg - 1) / kRbCfg;
+    // tiles: cfg_count / 32 of 32 configurations, then one per binary digit of the remainder (rs_tile)
+    const int gy = (cfg_count >> 5) + __builtin_popcount((unsigned)(cfg_count & 31));
     const long long n_chunks = (n_pts + kRsChunk - 1) / kRsChunk;
-    static const int waves = [] { const char *e = getenv("PVB_ROBOT_WAVES"); return e ? atoi(e) : 8; }();
+    static const int waves = [] { const char *e = getenv("PVB_ROBOT_WAVES"); return e ? atoi(e) : 4; }();
     long long gx = ((long long)sm_count() * 4 * waves + gy - 1) / gy;
     const long long gx_max = (n_chunks + kRsWarps - 1) / kRsWarps;
     if (gx > gx_max) gx = gx_max;
@@ -2305,11 +2325,15 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
         all_grid = descs[i].kind == PVB_KIND_GRID && !(descs[i].flags & (PVB_GRID_OOB_GT | PVB_GRID_TRILINEAR));
     const bool rb_filled = (cfg_count >= 16 && (double)cfg_count >= robot_fill * (double)(cm_tiles * kCmCfg)) ||
                            (tg && tg->vec && cfg_count >= 8) || (tg && tg->mc);
-    if (robot_kernel && cfg_major && all_grid && rb_filled) {
+    // the point-serial kernel has no fill problem (remainder configurations run in lane-split tiles): any batch of
+    // PVB_ROBOT_MIN_CFG or more configurations takes it
+    static const int serial_min_cfg = [] { const char *e = getenv("PVB_ROBOT_MIN_CFG"); return e ? atoi(e) : 8; }();
+    const bool serial_ok = robot_kernel >= 2 && n_sdf <= kRsMaxS && cfg_count >= serial_min_cfg;
+    if (robot_kernel && cfg_major && all_grid && (rb_filled || serial_ok)) {
         const int vec_rows = (tg ? tg->vec : (out_aligned && (n_pts % 4 == 0))) && aligned16(pts);
         // PVB_ROBOT_KERNEL: 2 (default) = point-serial nearest-sphere-first kernel for <= 8 links, 1 = the
         // 4-points-per-thread kernel, 0 = round 1's configuration-major kernel
-        if (robot_kernel >= 2 && n_sdf <= kRsMaxS)
+        if (serial_ok)
             return launch_robot_serial(descs, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, n_pts,
                                        (tg ? tg->vec : (out_aligned && (n_pts % 4 == 0))), out_val, out_grad, out_which,
                                        tg, s);

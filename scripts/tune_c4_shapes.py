@@ -13,7 +13,7 @@ iters = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 torch.cuda.set_device(0)
 wl = bench.make_workload("c4", 0, 1)
 res = {}
-for n in (200, 100, 50, 25):
+for n in (200, 100, 50, 25, 8, 3):
     fn = lambda i: wl.robot.sdf.query(wl.dev[i % 3], cfg_begin=0, cfg_count=n)      # noqa: E731
     for i in range(5):
         fn(i)
@@ -28,4 +28,5 @@ for n in (200, 100, 50, 25):
     res[n] = round(ts[len(ts) // 2], 4)
 print(json.dumps({"lib": os.path.basename(os.environ.get("PVB_LIB", "default")),
                   "robot_kernel": os.environ.get("PVB_ROBOT_KERNEL", "1"), "min_fill": os.environ.get("PVB_ROBOT_MIN_FILL"),
-                  "waves": os.environ.get("PVB_ROBOT_WAVES"), "ms_by_cfg_count": res}))
+                  "waves": os.environ.get("PVB_ROBOT_WAVES"), "min_cfg": os.environ.get("PVB_ROBOT_MIN_CFG"),
+                  "ms_by_cfg_count": res}))
