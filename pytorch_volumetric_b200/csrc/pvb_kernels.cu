@@ -1382,8 +1382,8 @@ template <int kDest>
 __global__ void __launch_bounds__(kRbCfg * kRsWarps, PVB_RS_MINB)
 robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, const float *__restrict__ xforms,
                     int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, int n_pts, int vec,
-                    float *__restrict__ out_val, float *__restrict__ out_grad, int *__restrict__ out_which,
-                    const __grid_constant__ OutTargets tg) {
+                    int steps_per_warp, float *__restrict__ out_val, float *__restrict__ out_grad,
+                    int *__restrict__ out_which, const __grid_constant__ OutTargets tg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1394,7 +1394,10 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
     const int cl = lane & (LC - 1), sub = lane >> lc_log2;    // this lane's configuration / point group
     const int pts_per_step = kRsChunk * SUB;                  // points a warp finishes between two flushes
     const int n_chunks = (n_pts + pts_per_step - 1) / pts_per_step;
-    if ((int)(blockIdx.x * kRsWarps) >= n_chunks) return;     // small tiles need fewer blocks (uniform per block)
+    // Balanced persistent schedule: the host sized steps_per_warp so that all tiles together fill the resident warp
+    // slots once; this tile gets as many blocks as its share needs and every warp runs at most steps_per_warp steps.
+    const int gx_tile = (n_chunks + kRsWarps * steps_per_warp - 1) / (kRsWarps * steps_per_warp);
+    if ((int)blockIdx.x >= gx_tile) return;                   // uniform per block
     // ---- stage the transforms of this configuration tile ----
     for (int item = threadIdx.x; item < LC * n_sdf; item += blockDim.x) {
         const int ci = item & (LC - 1), si = item >> lc_log2;
@@ -1434,7 +1437,7 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
     float *sv = &sm.sv[warp][0][0];                 // this warp's staging: LC rows x (8 SUB values | 24 SUB gradient floats)
     float *sg = &sm.sg[warp][0][0];
     const int vstride = pts_per_step + 1, gstride = 3 * pts_per_step + 1;     // odd: conflict-free STS.32 across lanes
-    for (int chunk = blockIdx.x * kRsWarps + warp; chunk < n_chunks; chunk += gridDim.x * kRsWarps) {
+    for (int chunk = blockIdx.x * kRsWarps + warp; chunk < n_chunks; chunk += gx_tile * kRsWarps) {
         const int pt_base = chunk * pts_per_step;
         const bool full = pt_base + pts_per_step <= n_pts;
 #pragma unroll 1
@@ -2245,26 +2248,37 @@ static int launch_robot_serial(const pvb_sdf_desc *descs, int n_sdf, const float
         pvb_set_error("pvb_composed_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
         return PVB_ERR_CUDA;
     }
-    // tiles: cfg_count / 32 of 32 configurations, then one per binary digit of the remainder (rs_tile)
-    const int gy = (cfg_count >> 5) + __builtin_popcount((unsigned)(cfg_count & 31));
-    const long long n_chunks = (n_pts + kRsChunk - 1) / kRsChunk;
-    static const int waves = [] { const char *e = getenv("PVB_ROBOT_WAVES"); return e ? atoi(e) : 4; }();
-    long long gx = ((long long)sm_count() * 4 * waves + gy - 1) / gy;
-    const long long gx_max = (n_chunks + kRsWarps - 1) / kRsWarps;
-    if (gx > gx_max) gx = gx_max;
+    // tiles: cfg_count / 32 of 32 configurations, then one per binary digit of the remainder (rs_tile).  A warp step
+    // is 8 points x (32 / LC) point groups; steps_per_warp is chosen so that the steps of all tiles together fill the
+    // resident warp slots (SMs x CTAs per SM x 8 warps) PVB_ROBOT_WAVES times: every warp runs the same number of
+    // steps (+-1) whatever the mix of tiles.
+    const int n_full = cfg_count >> 5, rem = cfg_count & 31;
+    const int gy = n_full + __builtin_popcount((unsigned)rem);
+    auto steps_of = [&](int lc_log2) { const long long per = (long long)kRsChunk << (5 - lc_log2); return (n_pts + per - 1) / per; };
+    long long total_steps = (long long)n_full * steps_of(5);
+    for (int b = 4; b >= 0; --b) if (rem & (1 << b)) total_steps += steps_of(b);
+    static const int waves = [] { const char *e = getenv("PVB_ROBOT_WAVES"); return e ? atoi(e) : 1; }();
+    const long long slots = (long long)sm_count() * PVB_RS_MINB * kRsWarps * (waves < 1 ? 1 : waves);
+    long long spw = (total_steps + slots - 1) / slots;
+    if (spw < 1) spw = 1;
+    long long gx = 1;
+    {
+        const long long widest = n_full ? steps_of(5) : steps_of(31 - __builtin_clz((unsigned)rem));
+        gx = (widest + kRsWarps * spw - 1) / (kRsWarps * spw);
+    }
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)gy);
     const OutTargets none{};
     timing_mark(0, stream);
     if (kind == 0)
         k0<<<grid, kRbCfg * kRsWarps, smem, stream>>>(pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, (int)n_pts,
-                                                      vec, out_val, out_grad, out_which, none);
+                                                      vec, (int)spw, out_val, out_grad, out_which, none);
     else if (kind == 1)
         k1<<<grid, kRbCfg * kRsWarps, smem, stream>>>(pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, (int)n_pts,
-                                                      vec, nullptr, nullptr, out_which, *tg);
+                                                      vec, (int)spw, nullptr, nullptr, out_which, *tg);
     else
         k2<<<grid, kRbCfg * kRsWarps, smem, stream>>>(pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, (int)n_pts,
-                                                      vec, nullptr, nullptr, out_which, *tg);
+                                                      vec, (int)spw, nullptr, nullptr, out_which, *tg);
     timing_mark(1, stream);
     PVB_CHECK_LAUNCH("pvb_composed_query(robot-serial)");
     return PVB_OK;
