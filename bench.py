@@ -368,6 +368,8 @@ class C4(Workload):
             return self.robot(pts)                                 # the public RobotSDF.__call__
         if self.mode == "peer":   # full result on every rank, written by the kernels themselves
             return self.pd.sharded_robot_query(self.robot, pts, gather="peer", result=self.peer)
+        if self.mode == "dma":    # slab evaluated locally, pushed to the peers by the copy engines (chunks overlap)
+            return self.pd.sharded_robot_query(self.robot, pts, gather="dma", result=self.peer)
         if self.mode == "mc":     # ... through the NVLS multicast mapping: one multimem.st reaches every rank
             return self.pd.sharded_robot_query(self.robot, pts, gather="multicast", result=self.peer)
         if self.mode == "nccl":   # full result on every rank: one NCCL all-gather per tensor
@@ -824,7 +826,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="default run: headline only")
-    ap.add_argument("--mode", default=None, choices=[None, "none", "nccl", "peer", "mc"],
+    ap.add_argument("--mode", default=None, choices=[None, "none", "nccl", "peer", "mc", "dma"],
                     help="C4 at N>1: force the re-assembly method of the headline instead of picking the faster one")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -880,6 +882,15 @@ def main():
             reassembly["peer_stores"] = {"ms_per_step": ms / sub_steps, "value": units_all * sub_steps / (ms * 1e-3),
                                          "nvlink_out_GBps_per_rank": remote / (ms / sub_steps * 1e-3) / 1e9,
                                          "nvlink_in_bytes_per_rank": remote, "buffers": wl.peer.backend}
+            slab = wl.end - wl.begin
+            for pieces in (1, 2, 4):         # copy-engine pushes: the slab at once, or in pieces that overlap the kernel
+                wl.peer.dma_chunk_cfgs = 0 if pieces == 1 else max(1, -(-slab // pieces))
+                wl.set_mode("dma")
+                ms, _, _ = timed_steps(wl.step, sub_steps, args.warmup, world)
+                reassembly[f"dma_push_{pieces}"] = {
+                    "ms_per_step": ms / sub_steps, "value": units_all * sub_steps / (ms * 1e-3),
+                    "chunk_cfgs": wl.peer.dma_chunk_cfgs or slab,
+                    "nvlink_ingest_GBps_per_rank": 16.0 * (units_all - wl.units) / (ms / sub_steps * 1e-3) / 1e9}
             if wl.peer.multicast:
                 wl.set_mode("mc")
                 ms, _, _ = timed_steps(wl.step, sub_steps, args.warmup, world)
@@ -893,7 +904,7 @@ def main():
             reassembly["peer_stores"] = {"unavailable": err}
             reassembly["multicast_stores"] = {"unavailable": err}
         for k in ("nccl_all_gather", "peer_stores", "multicast_stores"):
-            if "ms_per_step" in reassembly[k]:
+            if "ms_per_step" in reassembly.get(k, {}):
                 reassembly[k]["nvlink_ingest_GBps_per_rank"] = \
                     16.0 * (units_all - wl.units) / (reassembly[k]["ms_per_step"] * 1e-3) / 1e9
         reassembly["nvlink_peak_GBps_per_direction"] = 770.0      # B200_PROFILING.md
@@ -905,10 +916,20 @@ def main():
                 cands["peer"] = reassembly["peer_stores"]["ms_per_step"]
             if "ms_per_step" in reassembly["multicast_stores"]:
                 cands["mc"] = reassembly["multicast_stores"]["ms_per_step"]
+            dma = {k: v for k, v in reassembly.items() if k.startswith("dma_push") and "ms_per_step" in v}
+            if dma:
+                best_dma = min(dma, key=lambda k: dma[k]["ms_per_step"])
+                cands["dma"] = dma[best_dma]["ms_per_step"]
             chosen = min(cands, key=cands.get)
-        flag = torch.tensor([{"none": 0, "nccl": 1, "peer": 2, "mc": 3}[chosen]], device="cuda")     # rank 0 decides
+        flag = torch.tensor([{"none": 0, "nccl": 1, "peer": 2, "mc": 3, "dma": 4}[chosen]], device="cuda")     # rank 0 decides
+        chunk_flag = torch.tensor([0], device="cuda")
+        if chosen == "dma" and rank == 0:
+            chunk_flag[0] = int(dma[best_dma]["chunk_cfgs"]) if dma[best_dma]["chunk_cfgs"] < (wl.end - wl.begin) else 0
         torch.distributed.broadcast(flag, src=0)
-        chosen = ("none", "nccl", "peer", "mc")[int(flag.item())]
+        torch.distributed.broadcast(chunk_flag, src=0)
+        chosen = ("none", "nccl", "peer", "mc", "dma")[int(flag.item())]
+        if chosen == "dma":
+            wl.peer.dma_chunk_cfgs = int(chunk_flag.item())
         reassembly["chosen"] = chosen
         wl.set_mode(chosen)
 

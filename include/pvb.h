@@ -250,6 +250,9 @@ int pvb_ipc_free(void *ptr);
 int pvb_ipc_export(void *ptr, unsigned char *handle /* [PVB_IPC_HANDLE_BYTES] */);
 int pvb_ipc_open(const unsigned char *handle, void **out_ptr);
 int pvb_ipc_close(void *ptr);
+/* cudaMemcpyAsync between any two device pointers of the node (local or peer-mapped), on `stream`: the copy-engine
+ * push of a finished result slab into the peers' buffers (sharded_robot_query(gather="dma")). */
+int pvb_memcpy_async(void *dst, const void *src, int64_t bytes, void *stream);
 
 /* ---- batch_chamfer_dist, chamfer.py:79-94 ----
  * world_to_object DEVICE float[n_tf][16]; pts DEVICE [n_pts,3] world frame;

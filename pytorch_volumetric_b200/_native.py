@@ -156,6 +156,7 @@ _SIGNATURES = {
     "pvb_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "pvb_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "pvb_ipc_close": (ctypes.c_int, [ctypes.c_void_p]),
+    "pvb_memcpy_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "pvb_chamfer_workspace": (ctypes.c_int64, [ctypes.c_int64]),
     "pvb_chamfer": (ctypes.c_int, [ctypes.POINTER(SdfDesc), ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
                                    ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,

@@ -1394,10 +1394,12 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
     const int cl = lane & (LC - 1), sub = lane >> lc_log2;    // this lane's configuration / point group
     const int pts_per_step = kRsChunk * SUB;                  // points a warp finishes between two flushes
     const int n_chunks = (n_pts + pts_per_step - 1) / pts_per_step;
-    // Balanced persistent schedule: the host sized steps_per_warp so that all tiles together fill the resident warp
-    // slots once; this tile gets as many blocks as its share needs and every warp runs at most steps_per_warp steps.
-    const int gx_tile = (n_chunks + kRsWarps * steps_per_warp - 1) / (kRsWarps * steps_per_warp);
-    if ((int)blockIdx.x >= gx_tile) return;                   // uniform per block
+    // Blocks stride over the tile's steps; small tiles need fewer blocks than the grid is wide (uniform per block).
+    // (A balanced persistent schedule -- every warp exactly ceil(total steps / resident warp slots) steps -- measured
+    // 0.66 ms against 0.50 ms for this oversubscribed grid on C4: the cost of a point varies, and many short-lived
+    // blocks let the hardware scheduler even it out; profiles/r02/tune_c4_serial_balanced_schedule_rejected.jsonl.)
+    const int gx_tile = min((int)gridDim.x, (n_chunks + kRsWarps - 1) / kRsWarps);
+    if ((int)blockIdx.x >= gx_tile) return;
     // ---- stage the transforms of this configuration tile ----
     for (int item = threadIdx.x; item < LC * n_sdf; item += blockDim.x) {
         const int ci = item & (LC - 1), si = item >> lc_log2;
@@ -2248,25 +2250,15 @@ static int launch_robot_serial(const pvb_sdf_desc *descs, int n_sdf, const float
         pvb_set_error("pvb_composed_query: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
         return PVB_ERR_CUDA;
     }
-    // tiles: cfg_count / 32 of 32 configurations, then one per binary digit of the remainder (rs_tile).  A warp step
-    // is 8 points x (32 / LC) point groups; steps_per_warp is chosen so that the steps of all tiles together fill the
-    // resident warp slots (SMs x CTAs per SM x 8 warps) PVB_ROBOT_WAVES times: every warp runs the same number of
-    // steps (+-1) whatever the mix of tiles.
-    const int n_full = cfg_count >> 5, rem = cfg_count & 31;
-    const int gy = n_full + __builtin_popcount((unsigned)rem);
-    auto steps_of = [&](int lc_log2) { const long long per = (long long)kRsChunk << (5 - lc_log2); return (n_pts + per - 1) / per; };
-    long long total_steps = (long long)n_full * steps_of(5);
-    for (int b = 4; b >= 0; --b) if (rem & (1 << b)) total_steps += steps_of(b);
-    static const int waves = [] { const char *e = getenv("PVB_ROBOT_WAVES"); return e ? atoi(e) : 1; }();
-    const long long slots = (long long)sm_count() * PVB_RS_MINB * kRsWarps * (waves < 1 ? 1 : waves);
-    long long spw = (total_steps + slots - 1) / slots;
-    if (spw < 1) spw = 1;
-    long long gx = 1;
-    {
-        const long long widest = n_full ? steps_of(5) : steps_of(31 - __builtin_clz((unsigned)rem));
-        gx = (widest + kRsWarps * spw - 1) / (kRsWarps * spw);
-    }
+    // tiles: cfg_count / 32 of 32 configurations, then one per binary digit of the remainder (rs_tile)
+    const int gy = (cfg_count >> 5) + __builtin_popcount((unsigned)(cfg_count & 31));
+    const long long n_chunks = (n_pts + kRsChunk - 1) / kRsChunk;
+    static const int waves = [] { const char *e = getenv("PVB_ROBOT_WAVES"); return e ? atoi(e) : 4; }();
+    long long gx = ((long long)sm_count() * PVB_RS_MINB * waves + gy - 1) / gy;
+    const long long gx_max = (n_chunks + kRsWarps - 1) / kRsWarps;
+    if (gx > gx_max) gx = gx_max;
     if (gx < 1) gx = 1;
+    const long long spw = 0;            // (unused: schedule parameter of the rejected balanced variant)
     dim3 grid((unsigned)gx, (unsigned)gy);
     const OutTargets none{};
     timing_mark(0, stream);
@@ -2640,6 +2632,13 @@ extern "C" int pvb_fk_serial(const pvb_fk_frame *frames, int32_t n_frames, const
     if (n_cfg == 0) return PVB_OK;
     fk_serial_kernel<<<(n_cfg + 63) / 64, 64, 0, (cudaStream_t)stream>>>(plan, q, n_cfg, n_joints, out_xforms);
     PVB_CHECK_LAUNCH("pvb_fk_serial");
+    return PVB_OK;
+}
+
+extern "C" int pvb_memcpy_async(void *dst, const void *src, int64_t bytes, void *stream) {
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) { pvb_set_error("pvb_memcpy_async: invalid argument"); return PVB_ERR_INVALID; }
+    if (bytes == 0) return PVB_OK;
+    PVB_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream), "pvb_memcpy_async");
     return PVB_OK;
 }
 

@@ -282,6 +282,44 @@ class PeerResult:
         self._slot = (self._slot + 1) % self.SLOTS
         return self._targets[self._slot]
 
+    #: gather="dma": configurations per kernel launch / copy batch (0 = the whole slab at once); the pushes of chunk
+    #: k run on the copy engines while chunk k + 1 is being evaluated
+    dma_chunk_cfgs = 0
+
+    def dma_gather(self, comp, points, begin, end):
+        """Copy-engine re-assembly: the slab is evaluated into this rank's own buffer with the ordinary
+        single-destination kernel (in `dma_chunk_cfgs`-configuration pieces), and every finished piece is pushed to
+        each peer's buffer with cudaMemcpyAsync over the peer mappings, on side streams, while the next piece is being
+        evaluated.  The SMs never issue a remote store; NVLink carries large DMA packets."""
+        nat = self.nat
+        dev = self.device
+        P = self.n_pts
+        own_val, own_grad = self._targets[self._slot][0]
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = [torch.cuda.Stream(dev) for _ in range(max(1, min(self.world - 1, 4)))]
+        step = self.dma_chunk_cfgs if self.dma_chunk_cfgs > 0 else max(1, end - begin)
+        L = nat.lib()
+        with torch.cuda.device(dev):
+            for cb in range(begin, end, step):
+                cc = min(step, end - cb)
+                comp.query_at(points, own_val, own_grad, cfg_begin=cb, cfg_count=cc)
+                if self.world == 1:
+                    continue
+                done = torch.cuda.Event()
+                done.record(cur)
+                for k in range(1, self.world):                       # peers in ring order
+                    peer_val, peer_grad = self._targets[self._slot][k]
+                    st = self._copy_streams[(k - 1) % len(self._copy_streams)]
+                    st.wait_event(done)
+                    nat.check(L.pvb_memcpy_async(peer_val + 4 * cb * P, own_val + 4 * cb * P, 4 * cc * P, st.cuda_stream),
+                              "pvb_memcpy_async")
+                    nat.check(L.pvb_memcpy_async(peer_grad + 12 * cb * P, own_grad + 12 * cb * P, 12 * cc * P,
+                                                 st.cuda_stream), "pvb_memcpy_async")
+            if self.world > 1:
+                for st in self._copy_streams:
+                    cur.wait_stream(st)         # publish() below is ordered after every push of this rank
+
     def publish(self):
         """Stream-ordered barrier: when it completes on this rank, every rank's kernel (and with it all of its peer
         stores) has finished."""
@@ -323,13 +361,15 @@ def sharded_robot_query(robot_sdf, points, gather=True, group=None, result=None)
     begin, end = shard_range(n_cfg, rank, world)
     P = points.reshape(-1, 3).shape[0]
     if isinstance(gather, str):
-        if gather not in ("peer", "multicast") or result is None:
-            raise ValueError('gather must be True, False, "peer" or "multicast" (the latter two with '
+        if gather not in ("peer", "multicast", "dma") or result is None:
+            raise ValueError('gather must be True, False, "peer", "multicast" or "dma" (the latter three with '
                              'result=PeerResult(...))')
         if (result.n_cfg, result.n_pts) != (n_cfg, P):
             raise ValueError(f"PeerResult is ({result.n_cfg}, {result.n_pts}), the query is ({n_cfg}, {P})")
         targets = result.next_slot()
-        if gather == "multicast":
+        if gather == "dma":
+            result.dma_gather(comp, points, begin, end)
+        elif gather == "multicast":
             if not result.multicast:
                 raise RuntimeError("this PeerResult has no multicast mapping (needs backend='symm' on an NVSwitch fabric)")
             comp.query_multicast(points, *result.multicast_target(), cfg_begin=begin, cfg_count=end - begin)

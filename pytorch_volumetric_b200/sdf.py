@@ -609,6 +609,28 @@ class ComposedSDF(ObjectFrameSDF):
                                                          ctypes.cast(arr, ctypes.c_void_p), len(targets), None,
                                                          nat.stream_ptr(device)), "pvb_composed_query_multi")
 
+    def query_at(self, points_in_object_frame, val_addr, grad_addr, cfg_begin=0, cfg_count=None):
+        """`query` that writes the slab into caller-owned device memory: val_addr / grad_addr are the addresses of
+        FULL (n_cfg * P) value / gradient buffers (float32); the slab lands at element cfg_begin * P.  Single
+        destination, the kernels' fastest store path -- what the copy-engine re-assembly (gather="dma") runs before it
+        pushes the slab to the peers."""
+        S = len(self.sdfs)
+        n_cfg = 1 if self.tsf_batch is None else math.prod(list(self.tsf_batch))
+        if cfg_count is None:
+            cfg_count = n_cfg - cfg_begin
+        device = nat.compute_device(points_in_object_frame.device if torch.is_tensor(points_in_object_frame) else None)
+        with torch.cuda.device(device):
+            p = nat.as_f32_points(points_in_object_frame, device)
+            P = p.shape[0]
+            descs_arr, needs_mesh = self._native_descs(device)
+            if descs_arr is None:
+                raise NotImplementedError("query_at needs sub-SDFs with native descriptors (mesh / cached / sphere)")
+            xf = self._xforms_on(device)
+            nat.check(nat.lib().pvb_composed_query(descs_arr, S, int(needs_mesh), nat.ptr(xf), n_cfg, cfg_begin,
+                                                   cfg_count, nat.ptr(p), P, nat.PVB_MESH_DEFAULT,
+                                                   int(val_addr) + 4 * cfg_begin * P, int(grad_addr) + 12 * cfg_begin * P,
+                                                   None, nat.stream_ptr(device)), "pvb_composed_query")
+
     def query_multicast(self, points_in_object_frame, mc_val, mc_grad, cfg_begin=0, cfg_count=None):
         """`query` whose result slab leaves through an NVLS multicast mapping (pvb_composed_query_multicast): mc_val /
         mc_grad are the multicast device addresses of the full (n_cfg * P) value / gradient buffers; one multimem.st

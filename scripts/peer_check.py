@@ -77,6 +77,11 @@ def main():
             for rep in range(3):
                 v, g = pd.sharded_robot_query(robot, pts, gather="multicast", result=res)
                 ok = check(f"multicast_{rep}", v, g) and ok
+        for pieces in (1, 3):
+            res.dma_chunk_cfgs = 0 if pieces == 1 else max(1, -(-(endc - begin) // pieces))
+            for rep in range(2):
+                v, g = pd.sharded_robot_query(robot, pts, gather="dma", result=res)
+                ok = check(f"dma_{backend}_{pieces}_{rep}", v, g) and ok
         results[backend + "_multicast"] = bool(res.multicast)
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -89,6 +94,10 @@ def main():
         if res.multicast:
             times["ms_multicast_stores"] = timed(
                 lambda: pd.sharded_robot_query(robot, pts, gather="multicast", result=res), steps)
+        for pieces in (1, 2, 4):
+            res.dma_chunk_cfgs = 0 if pieces == 1 else max(1, -(-(endc - begin) // pieces))
+            times[f"ms_dma_push_{backend}_{pieces}"] = timed(
+                lambda: pd.sharded_robot_query(robot, pts, gather="dma", result=res), steps)
     for res in peers.values():
         res.close()
     if rank == 0:
@@ -98,7 +107,7 @@ def main():
         line.update(times)
         line.update(results)
         for k, t in times.items():
-            if k.startswith("ms_peer") or k.startswith("ms_multicast") or k.startswith("ms_nccl"):
+            if k.startswith(("ms_peer", "ms_multicast", "ms_nccl", "ms_dma")):
                 line[k.replace("ms_", "nvlink_ingest_GBps_")] = remote / (t * 1e-3) / 1e9
         print(json.dumps(line))
         if flag.item() == 1.0:
