@@ -6,9 +6,6 @@ N=${1:-2}
 OUT=gpurun_out/r02d_n$N
 mkdir -p "$OUT"
 export NCCL_DEBUG=WARN
-T="$OUT/tune_c4.jsonl"; : > "$T"
-for w in 1 2 4; do CUDA_VISIBLE_DEVICES=0 PVB_ROBOT_WAVES=$w timeout 300 python scripts/tune_c4_shapes.py 30 2>>"$OUT/tune.err" | grep '^{' >> "$T"; done
-cat "$T"
 if [ "$N" = "2" ]; then
   timeout 600 python -m pytest tests/test_gpu_peer.py -m gpu -x -q > "$OUT/pytest_peer.log" 2>&1; echo "pytest rc=$?" >> "$OUT/pytest_peer.log"
   tail -5 "$OUT/pytest_peer.log"
