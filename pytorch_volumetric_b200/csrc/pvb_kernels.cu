@@ -1382,7 +1382,7 @@ template <int kDest>
 __global__ void __launch_bounds__(kRbCfg * kRsWarps, PVB_RS_MINB)
 robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, const float *__restrict__ xforms,
                     int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, int n_pts, int vec,
-                    int steps_per_warp, float *__restrict__ out_val, float *__restrict__ out_grad,
+                    int chunk_log2, float *__restrict__ out_val, float *__restrict__ out_grad,
                     int *__restrict__ out_which, const __grid_constant__ OutTargets tg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
@@ -1392,7 +1392,11 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
     const int LC = 1 << lc_log2;                              // configurations of this tile = lanes per point group
     const int sub_log2 = 5 - lc_log2, SUB = 1 << sub_log2;    // point groups per warp
     const int cl = lane & (LC - 1), sub = lane >> lc_log2;    // this lane's configuration / point group
-    const int pts_per_step = kRsChunk * SUB;                  // points a warp finishes between two flushes
+    // points per point group between two flushes: 8 (whole 32-byte sectors of values per row), or 4 when the launch has
+    // so few steps per resident warp that the serial chain of one step (8 points x ~4 dependent gathers) is the critical
+    // path -- the 25-configuration slab of an 8-GPU split
+    const int chunk = 1 << chunk_log2;
+    const int pts_per_step = chunk * SUB;                     // points a warp finishes between two flushes
     const int n_chunks = (n_pts + pts_per_step - 1) / pts_per_step;
     // Blocks stride over the tile's steps; small tiles need fewer blocks than the grid is wide (uniform per block).
     // (A balanced persistent schedule -- every warp exactly ceil(total steps / resident warp slots) steps -- measured
@@ -1443,8 +1447,8 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
         const int pt_base = chunk * pts_per_step;
         const bool full = pt_base + pts_per_step <= n_pts;
 #pragma unroll 1
-        for (int k = 0; k < kRsChunk; ++k) {
-            const int pt = pt_base + sub * kRsChunk + k;
+        for (int k = 0; k < chunk; ++k) {
+            const int pt = pt_base + sub * chunk + k;
             const bool on = pt < n_pts;
             if (!full && !__any_sync(0xffffffffu, on)) break;
             const f3 p = on ? load_point(pts, pt) : mk3(0.f, 0.f, 0.f);     // the same for the LC lanes of a point group
@@ -1491,7 +1495,7 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
             }
             const int sb = max(bs, 0);
             const f3 go = composed_rotate_back(sm.xf[cl][3 * sb], sm.xf[cl][3 * sb + 1], sm.xf[cl][3 * sb + 2], bg);
-            const int col = sub * kRsChunk + k;
+            const int col = sub * chunk + k;
             sv[cl * vstride + col] = best;
             sg[cl * gstride + 3 * col] = go.x;
             sg[cl * gstride + 3 * col + 1] = go.y;
@@ -1501,15 +1505,18 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
         __syncwarp();
         // ---- flush: LC configuration rows x (8 SUB values | 24 SUB gradient floats), all whole 32-byte sectors ----
         if (vec && full) {
-            // 256 chunks of 16 B per warp step: the first 64 are values, the other 192 gradients; lane i takes i, i + 32, ...
-            const int vper = 2 << sub_log2, gper = 6 << sub_log2;        // chunks per row
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            // 32 * chunk pieces of 16 B per warp step: the first quarter values, the rest gradients; lane i takes i, i + 32, ...
+            const int vper_log2 = chunk_log2 - 2 + sub_log2;             // value pieces per row = (chunk / 4) * SUB
+            const int gunit = 3 << (chunk_log2 - 2);                     // gradient pieces per row and point group
+            const int gper = gunit << sub_log2;
+            const int n_val = 8 << chunk_log2;                           // value pieces of the warp step
+#pragma unroll 1
+            for (int j = 0; j < chunk; ++j) {
                 const int c = lane + 32 * j;
-                const bool is_val = j < 2;
-                const int g = is_val ? c : c - 64;
-                const int row = is_val ? g >> (1 + sub_log2) : (g >> sub_log2) / 6;
-                const int part = is_val ? g & (vper - 1) : g - row * gper;
+                const bool is_val = c < n_val;
+                const int g = is_val ? c : c - n_val;
+                const int row = is_val ? g >> vper_log2 : (g >> sub_log2) / gunit;
+                const int part = is_val ? g & ((1 << vper_log2) - 1) : g - row * gper;
                 const float *src = is_val ? sv + row * vstride + 4 * part : sg + row * gstride + 4 * part;
                 const float4 v4 = make_float4(src[0], src[1], src[2], src[3]);
                 const size_t o_row = (size_t)(c0 + row) * n_pts + pt_base;
@@ -1524,8 +1531,8 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
                 }
             }
         } else {
-            for (int k = 0; k < kRsChunk; ++k) {
-                const int col = sub * kRsChunk + k;
+            for (int k = 0; k < chunk; ++k) {
+                const int col = sub * chunk + k;
                 const int pt = pt_base + col;
                 if (pt >= n_pts) break;
                 const float v = sv[cl * vstride + col];
@@ -2251,14 +2258,22 @@ static int launch_robot_serial(const pvb_sdf_desc *descs, int n_sdf, const float
         return PVB_ERR_CUDA;
     }
     // tiles: cfg_count / 32 of 32 configurations, then one per binary digit of the remainder (rs_tile)
-    const int gy = (cfg_count >> 5) + __builtin_popcount((unsigned)(cfg_count & 31));
-    const long long n_chunks = (n_pts + kRsChunk - 1) / kRsChunk;
+    const int n_full = cfg_count >> 5, rem = cfg_count & 31;
+    const int gy = n_full + __builtin_popcount((unsigned)rem);
+    // steps per resident warp slot at 8 points per step; below PVB_ROBOT_FINE_STEPS the launch runs 4-point steps
+    auto steps_of = [&](int lc_log2) { const long long per = (long long)kRsChunk << (5 - lc_log2); return (n_pts + per - 1) / per; };
+    long long total_steps = (long long)n_full * steps_of(5);
+    for (int b = 4; b >= 0; --b) if (rem & (1 << b)) total_steps += steps_of(b);
+    static const int fine_below = [] { const char *e = getenv("PVB_ROBOT_FINE_STEPS"); return e ? atoi(e) : 6; }();
+    const long long slots = (long long)sm_count() * PVB_RS_MINB * kRsWarps;
+    const int chunk_log2 = (total_steps < (long long)fine_below * slots) ? 2 : 3;
+    const long long n_chunks = (n_pts + (1 << chunk_log2) - 1) >> chunk_log2;     // steps of a 32-configuration tile
     static const int waves = [] { const char *e = getenv("PVB_ROBOT_WAVES"); return e ? atoi(e) : 4; }();
     long long gx = ((long long)sm_count() * PVB_RS_MINB * waves + gy - 1) / gy;
     const long long gx_max = (n_chunks + kRsWarps - 1) / kRsWarps;
     if (gx > gx_max) gx = gx_max;
     if (gx < 1) gx = 1;
-    const long long spw = 0;            // (unused: schedule parameter of the rejected balanced variant)
+    const long long spw = chunk_log2;
     dim3 grid((unsigned)gx, (unsigned)gy);
     const OutTargets none{};
     timing_mark(0, stream);

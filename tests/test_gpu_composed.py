@@ -314,8 +314,11 @@ def test_robot_kernel_equals_point_major_and_ragged(tmp_path):
                     link_sdf_cls=pv.cache_link_sdf_factory(resolution=0.02, padding=1.0, device="cuda",
                                                            cache_path=str(tmp_path / "arm.pkl")))
     lo = [r[0] for r in workloads.ARM_QUERY_RANGE]; hi = [r[1] for r in workloads.ARM_QUERY_RANGE]
-    base = workloads.uniform_points(4200, lo, hi, seed=9).cuda()
-    for n_cfg, n_pts, shift in ((64, 4096, 0), (40, 4100, 0), (33, 1001, 0), (32, 2048, 1)):
+    base = workloads.uniform_points(100_004, lo, hi, seed=9).cuda()
+    # small launches run 4-point warp steps, the 200 x 100 000 one (bench.py's C4) 8-point steps; 25 = 16 + 8 + 1 and
+    # 200 = 6 x 32 + 8 exercise the lane-split remainder tiles
+    for n_cfg, n_pts, shift in ((64, 4096, 0), (40, 4100, 0), (33, 1001, 0), (32, 2048, 1), (25, 4096, 0),
+                                (200, 100_000, 0), (31, 100_003, 1)):
         s.set_joint_configuration(workloads.arm_configurations(n_cfg).cuda())
         pts = base.reshape(-1)[3 * shift:3 * (shift + n_pts)].view(n_pts, 3)       # shift=1: not 16-byte aligned
         v, g, w = s.sdf.query(pts, return_which=True)                               # >= 16 configurations: robot kernel
