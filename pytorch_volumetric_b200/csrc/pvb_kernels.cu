@@ -1395,8 +1395,8 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
     // points per point group between two flushes: 8 (whole 32-byte sectors of values per row), or 4 when the launch has
     // so few steps per resident warp that the serial chain of one step (8 points x ~4 dependent gathers) is the critical
     // path -- the 25-configuration slab of an 8-GPU split
-    const int chunk = 1 << chunk_log2;
-    const int pts_per_step = chunk * SUB;                     // points a warp finishes between two flushes
+    const int npt = 1 << chunk_log2;                          // points per point group and step (4 or 8)
+    const int pts_per_step = npt * SUB;                     // points a warp finishes between two flushes
     const int n_chunks = (n_pts + pts_per_step - 1) / pts_per_step;
     // Blocks stride over the tile's steps; small tiles need fewer blocks than the grid is wide (uniform per block).
     // (A balanced persistent schedule -- every warp exactly ceil(total steps / resident warp slots) steps -- measured
@@ -1447,8 +1447,8 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
         const int pt_base = chunk * pts_per_step;
         const bool full = pt_base + pts_per_step <= n_pts;
 #pragma unroll 1
-        for (int k = 0; k < chunk; ++k) {
-            const int pt = pt_base + sub * chunk + k;
+        for (int k = 0; k < npt; ++k) {
+            const int pt = pt_base + sub * npt + k;
             const bool on = pt < n_pts;
             if (!full && !__any_sync(0xffffffffu, on)) break;
             const f3 p = on ? load_point(pts, pt) : mk3(0.f, 0.f, 0.f);     // the same for the LC lanes of a point group
@@ -1495,7 +1495,7 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
             }
             const int sb = max(bs, 0);
             const f3 go = composed_rotate_back(sm.xf[cl][3 * sb], sm.xf[cl][3 * sb + 1], sm.xf[cl][3 * sb + 2], bg);
-            const int col = sub * chunk + k;
+            const int col = sub * npt + k;
             sv[cl * vstride + col] = best;
             sg[cl * gstride + 3 * col] = go.x;
             sg[cl * gstride + 3 * col + 1] = go.y;
@@ -1511,7 +1511,7 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
             const int gper = gunit << sub_log2;
             const int n_val = 8 << chunk_log2;                           // value pieces of the warp step
 #pragma unroll 1
-            for (int j = 0; j < chunk; ++j) {
+            for (int j = 0; j < npt; ++j) {
                 const int c = lane + 32 * j;
                 const bool is_val = c < n_val;
                 const int g = is_val ? c : c - n_val;
@@ -1531,8 +1531,8 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
                 }
             }
         } else {
-            for (int k = 0; k < chunk; ++k) {
-                const int col = sub * chunk + k;
+            for (int k = 0; k < npt; ++k) {
+                const int col = sub * npt + k;
                 const int pt = pt_base + col;
                 if (pt >= n_pts) break;
                 const float v = sv[cl * vstride + col];
