@@ -2264,7 +2264,9 @@ static int launch_robot_serial(const pvb_sdf_desc *descs, int n_sdf, const float
     auto steps_of = [&](int lc_log2) { const long long per = (long long)kRsChunk << (5 - lc_log2); return (n_pts + per - 1) / per; };
     long long total_steps = (long long)n_full * steps_of(5);
     for (int b = 4; b >= 0; --b) if (rem & (1 << b)) total_steps += steps_of(b);
-    static const int fine_below = [] { const char *e = getenv("PVB_ROBOT_FINE_STEPS"); return e ? atoi(e) : 6; }();
+    // (C4 slabs, ms at 8 / 4 points per step: 25 configurations 0.133 / 0.116, 50: 0.177 / 0.162, 100: 0.280 / 0.273, 200:
+    // 0.497 / 0.517 -- profiles/r02/tune_c4_fine_steps.jsonl)
+    static const int fine_below = [] { const char *e = getenv("PVB_ROBOT_FINE_STEPS"); return e ? atoi(e) : 12; }();
     const long long slots = (long long)sm_count() * PVB_RS_MINB * kRsWarps;
     const int chunk_log2 = (total_steps < (long long)fine_below * slots) ? 2 : 3;
     const long long n_chunks = (n_pts + (1 << chunk_log2) - 1) >> chunk_log2;     // steps of a 32-configuration tile

@@ -1,0 +1,43 @@
+"""After `scripts/profile_round.sh <round>` ran on the GPU box: summarise every .ncu-rep of gpurun_out/<round>/ into
+profiles/<round>/*.ncu.json, copy the bench lines / launch list, and refresh profiles/ncu_traffic.json (DRAM bytes per
+launch of each workload's dominant kernel, read by bench.py into roofline.traffic).
+usage: python scripts/collect_profiles.py r02"""
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+rnd = sys.argv[1] if len(sys.argv) > 1 else "r02"
+src = os.path.join(ROOT, "gpurun_out", rnd)
+dst = os.path.join(ROOT, "profiles", rnd)
+os.makedirs(dst, exist_ok=True)
+WORKLOAD_OF = {"robot_serial_c4": "c4", "grid_lookup_tma_c2": "c2", "composed_query_c3": "c3",
+               "composed_query_c3cached": "c3cached", "mesh_query_mesh10k": "mesh10k", "chamfer_partial_c5": "c5"}
+traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+for f in sorted(os.listdir(src)):
+    p = os.path.join(src, f)
+    if f.endswith(".ncu-rep"):
+        name = f[:-8]
+        out = os.path.join(dst, name + ".ncu.json")
+        subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), p, out], stdout=subprocess.DEVNULL)
+        raw = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True,
+                             stderr=subprocess.DEVNULL).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        if len(rows) > 2 and name in WORKLOAD_OF:
+            idx = {h: i for i, h in enumerate(rows[0])}
+            unit = {h: u for h, u in zip(rows[0], rows[1])}
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(rows[2][idx[k]])
+                tot += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit[k]]
+            traffic[WORKLOAD_OF[name]] = int(tot)
+        print("summarised", f)
+    elif f.endswith((".jsonl", ".csv")) or f.startswith("pytest"):
+        shutil.copy(p, os.path.join(dst, f))
+json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
+print("ncu_traffic.json:", traffic)

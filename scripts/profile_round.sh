@@ -1,13 +1,9 @@
 #!/bin/bash
 # One GPU-box call that refreshes the judged evidence of a round.  Run from the repo root ON THE GPU BOX:
 #
-#   gpurun --timeout 900 -- 'bash scripts/profile_round.sh r02'
+#   gpurun --timeout 1800 -- 'bash scripts/profile_round.sh r02'
 #
-# and afterwards, in the build container:
-#
-#   for f in gpurun_out/r02/*.ncu-rep; do python scripts/ncu_summary.py $f profiles/r02/$(basename ${f%.ncu-rep}).ncu.json; done
-#   cp gpurun_out/r02/*.jsonl gpurun_out/r02/*.csv profiles/r02/
-#
+# and afterwards, in the build container:  python scripts/collect_profiles.py r02
 # Numbers printed by anything that ran under ncu are never bench values: the .jsonl files come from separate runs.
 set -u
 R=${1:-r02}
@@ -15,24 +11,30 @@ OUT=gpurun_out/$R
 mkdir -p "$OUT"
 NCU="ncu --set full --clock-control none --import-source on"
 
-# 1. bench lines (not under a profiler)
-python bench.py                         2>/dev/null | grep '^{' | tail -1 > "$OUT/bench_default_1gpu.jsonl"
-for w in mesh10k c3 c3cached c4 c4readme c5; do
-    timeout 300 python bench.py --workload $w --steps 30 --no-cpu-baseline 2>/dev/null | grep '^{' | tail -1
-done > "$OUT/bench_workloads_1gpu.jsonl"
+# 0. the GPU test tier
+timeout 1500 python -m pytest tests -m gpu -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" >> "$OUT/pytest_gpu.log"
+tail -4 "$OUT/pytest_gpu.log"
+
+# 1. the default bench line (not under a profiler): headline C4 + every other BASELINE config + CPU baselines
+timeout 1200 python bench.py --steps 20 --warmup 5 2> "$OUT/bench_default.err" | grep '^{' | tail -1 > "$OUT/bench_default_1gpu.jsonl"
+timeout 600 python bench.py --impl reference --steps 20 --warmup 5 2> "$OUT/bench_reference.err" | grep '^{' | tail -1 > "$OUT/bench_reference.jsonl"
+timeout 300 python bench.py --workload c4readme --steps 50 --no-cpu-baseline 2>/dev/null | grep '^{' | tail -1 > "$OUT/bench_c4readme.jsonl"
+timeout 300 python bench.py --workload mesh50k --steps 20 --no-cpu-baseline 2>/dev/null | grep '^{' | tail -1 > "$OUT/bench_mesh50k.jsonl"
 
 # 2. launch list of the default bench command (per-launch device times, cold cache, serialised)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_bench_c2.csv" \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file "$OUT/launches_bench_default.csv" \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 
 # 3. one full capture per dominant kernel (a single launch each: ncu replays it ~40 times)
 capture() {   # name, kernel regex, workload
-    timeout 600 $NCU -k "regex:$2" -s 3 -c 1 -o "$OUT/$1" -f \
+    timeout 500 $NCU -k "regex:$2" -s 3 -c 1 -o "$OUT/$1" -f \
         python bench.py --workload "$3" --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > "$OUT/$1.log" 2>&1
 }
-capture grid_lookup_tma      grid_lookup_tma_kernel      c2
-capture composed_cfgmajor_c4 composed_cfgmajor_kernel    c4
+capture robot_serial_c4      robot_serial_kernel         c4
+capture grid_lookup_tma_c2   grid_lookup_tma_kernel      c2
 capture composed_query_c3    composed_query_kernel       c3
-capture mesh_query           mesh_query_kernel           mesh10k
+capture composed_query_c3cached composed_query_kernel    c3cached
+capture mesh_query_mesh10k   mesh_query_kernel           mesh10k
 capture chamfer_partial_c5   chamfer_partial_kernel      c5
+cp pytorch_volumetric_b200/csrc/libpvb.so "$OUT/libpvb_$R.so"
 ls -la "$OUT"
