@@ -21,13 +21,9 @@ traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
 for f in sorted(os.listdir(src)):
     p = os.path.join(src, f)
-    if f.endswith(".ncu-rep"):
+    if f.endswith(".raw.csv"):          # raw metric page written on the box (the report itself may not have travelled)
         name = f[:-8]
-        out = os.path.join(dst, name + ".ncu.json")
-        subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), p, out], stdout=subprocess.DEVNULL)
-        raw = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True,
-                             stderr=subprocess.DEVNULL).stdout
-        rows = list(csv.reader(io.StringIO(raw)))
+        rows = list(csv.reader(io.StringIO(open(p).read())))
         if len(rows) > 2 and name in WORKLOAD_OF:
             idx = {h: i for i, h in enumerate(rows[0])}
             unit = {h: u for h, u in zip(rows[0], rows[1])}
@@ -37,7 +33,7 @@ for f in sorted(os.listdir(src)):
                 tot += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit[k]]
             traffic[WORKLOAD_OF[name]] = int(tot)
         print("summarised", f)
-    elif f.endswith((".jsonl", ".csv")) or f.startswith("pytest"):
+    elif f.endswith((".jsonl", ".csv", ".ncu.json")) or f.startswith("pytest"):
         shutil.copy(p, os.path.join(dst, f))
 json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 print("ncu_traffic.json:", traffic)

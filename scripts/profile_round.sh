@@ -26,9 +26,15 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 
 # 3. one full capture per dominant kernel (a single launch each: ncu replays it ~40 times)
+# (gpurun brings back at most 64 MiB: every report is summarised on the box -- scripts/ncu_summary.py, plus the raw
+#  metric page as csv -- and only the report named in KEEP_REP travels)
+KEEP_REP=${KEEP_REP:-robot_serial_c4}
 capture() {   # name, kernel regex, workload
     timeout 500 $NCU -k "regex:$2" -s 3 -c 1 -o "$OUT/$1" -f \
         python bench.py --workload "$3" --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > "$OUT/$1.log" 2>&1
+    python scripts/ncu_summary.py "$OUT/$1.ncu-rep" "$OUT/$1.ncu.json" > /dev/null 2>&1
+    ncu -i "$OUT/$1.ncu-rep" --page raw --csv > "$OUT/$1.raw.csv" 2>/dev/null
+    [ "$1" = "$KEEP_REP" ] || rm -f "$OUT/$1.ncu-rep"
 }
 capture robot_serial_c4      robot_serial_kernel         c4
 capture grid_lookup_tma_c2   grid_lookup_tma_kernel      c2
@@ -36,5 +42,6 @@ capture composed_query_c3    composed_query_kernel       c3
 capture composed_query_c3cached composed_query_kernel    c3cached
 capture mesh_query_mesh10k   mesh_query_kernel           mesh10k
 capture chamfer_partial_c5   chamfer_partial_kernel      c5
-cp pytorch_volumetric_b200/csrc/libpvb.so "$OUT/libpvb_$R.so"
+[ -f "$OUT/$KEEP_REP.ncu-rep" ] && cp pytorch_volumetric_b200/csrc/libpvb.so "$OUT/libpvb_$R.so"
+du -sh "$OUT"
 ls -la "$OUT"
