@@ -1440,14 +1440,28 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
         sm.sph[ci][si] = sp;
     }
     __syncthreads();
-    float *sv = &sm.sv[warp][0][0];                 // this warp's staging: LC rows x (8 SUB values | 24 SUB gradient floats)
-    float *sg = &sm.sg[warp][0][0];
-    const int vstride = pts_per_step + 1, gstride = 3 * pts_per_step + 1;     // odd: conflict-free STS.32 across lanes
-    for (int chunk = blockIdx.x * kRsWarps + warp; chunk < n_chunks; chunk += gx_tile * kRsWarps) {
+    // Staging tile.  One destination in local memory (kDest 0): every warp owns a tile of LC rows x its own
+    // pts_per_step points and flushes it alone (__syncwarp only).  Remote destinations (peer buffers, multicast): the 8
+    // warps of the block share ONE tile of LC rows x 8 pts_per_step points and flush it together, so that a row leaves
+    // as 256 contiguous bytes of values + 768 of gradients -- stores into peer memory run at 431 GB/s in 32-byte
+    // segments, 569 in 64-byte ones and 696 GB/s from 128 bytes up (scripts/ubench_peer_store.cu,
+    // profiles/r02/ubench_peer_store.jsonl); the two block barriers per step are the price.
+    constexpr bool kCoop = kDest != 0;
+    constexpr int w_log2 = kCoop ? 3 : 0;                                   // log2(warps sharing a tile)
+    float *sv = kCoop ? &sm.sv[0][0][0] : &sm.sv[warp][0][0];
+    float *sg = kCoop ? &sm.sg[0][0][0] : &sm.sg[warp][0][0];
+    const int row_pts = pts_per_step << w_log2;                             // points per row of the tile
+    const int vstride = row_pts + 1, gstride = 3 * row_pts + 1;             // odd: conflict-free STS.32 across lanes
+    const int col0 = (kCoop ? warp * pts_per_step : 0) + sub * npt;         // this lane's first column
+    const int n_super = (n_chunks + kRsWarps - 1) / kRsWarps;
+    for (int sup = blockIdx.x; sup < n_super; sup += gx_tile) {
+        const int chunk = sup * kRsWarps + warp;
+        const bool active = chunk < n_chunks;                               // uniform per warp
         const int pt_base = chunk * pts_per_step;
-        const bool full = pt_base + pts_per_step <= n_pts;
+        const int tile_base = kCoop ? sup * kRsWarps * pts_per_step : pt_base;
+        const bool full = tile_base + row_pts <= n_pts;                     // every point of the tile exists
 #pragma unroll 1
-        for (int k = 0; k < npt; ++k) {
+        for (int k = 0; k < (active ? npt : 0); ++k) {
             const int pt = pt_base + sub * npt + k;
             const bool on = pt < n_pts;
             if (!full && !__any_sync(0xffffffffu, on)) break;
@@ -1495,31 +1509,34 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
             }
             const int sb = max(bs, 0);
             const f3 go = composed_rotate_back(sm.xf[cl][3 * sb], sm.xf[cl][3 * sb + 1], sm.xf[cl][3 * sb + 2], bg);
-            const int col = sub * npt + k;
+            const int col = col0 + k;
             sv[cl * vstride + col] = best;
             sg[cl * gstride + 3 * col] = go.x;
             sg[cl * gstride + 3 * col + 1] = go.y;
             sg[cl * gstride + 3 * col + 2] = go.z;
             if (out_which && on) out_which[(size_t)(c0 + cl) * n_pts + pt] = bs;
         }
-        __syncwarp();
-        // ---- flush: LC configuration rows x (8 SUB values | 24 SUB gradient floats), all whole 32-byte sectors ----
+        if constexpr (kCoop) __syncthreads(); else __syncwarp();
+        // ---- flush: LC configuration rows x (row_pts values | 3 row_pts gradient floats), whole sectors ----
         if (vec && full) {
-            // 32 * chunk pieces of 16 B per warp step: the first quarter values, the rest gradients; lane i takes i, i + 32, ...
-            const int vper_log2 = chunk_log2 - 2 + sub_log2;             // value pieces per row = (chunk / 4) * SUB
-            const int gunit = 3 << (chunk_log2 - 2);                     // gradient pieces per row and point group
+            // LC * row_pts pieces of 16 B per tile: the first quarter values, the rest gradients; the tile's threads take
+            // consecutive pieces (one row segment per warp instruction), npt pieces each
+            const int vper_log2 = w_log2 + chunk_log2 - 2 + sub_log2;    // value pieces per row = row_pts / 4
+            const int gunit = 3 << (w_log2 + chunk_log2 - 2);            // gradient pieces per row and point group
             const int gper = gunit << sub_log2;
-            const int n_val = 8 << chunk_log2;                           // value pieces of the warp step
+            const int n_val = 8 << (w_log2 + chunk_log2);                // value pieces of the tile = LC * row_pts / 4
+            const int me = kCoop ? (int)threadIdx.x : lane;
+            constexpr int kGroup = kCoop ? kRbCfg * kRsWarps : 32;
 #pragma unroll 1
             for (int j = 0; j < npt; ++j) {
-                const int c = lane + 32 * j;
+                const int c = me + kGroup * j;
                 const bool is_val = c < n_val;
                 const int g = is_val ? c : c - n_val;
                 const int row = is_val ? g >> vper_log2 : (g >> sub_log2) / gunit;
                 const int part = is_val ? g & ((1 << vper_log2) - 1) : g - row * gper;
                 const float *src = is_val ? sv + row * vstride + 4 * part : sg + row * gstride + 4 * part;
                 const float4 v4 = make_float4(src[0], src[1], src[2], src[3]);
-                const size_t o_row = (size_t)(c0 + row) * n_pts + pt_base;
+                const size_t o_row = (size_t)(c0 + row) * n_pts + tile_base;
                 const size_t off = is_val ? o_row + 4 * part : 3 * o_row + 4 * part;
                 if constexpr (kDest == 0) {
                     __stcs(reinterpret_cast<float4 *>((is_val ? out_val : out_grad) + off), v4);
@@ -1530,10 +1547,10 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
                     st_mc_v4((is_val ? tg.val[0] : tg.grad[0]) + off, v4);
                 }
             }
-        } else {
+        } else if (active) {
             for (int k = 0; k < npt; ++k) {
-                const int col = sub * npt + k;
-                const int pt = pt_base + col;
+                const int col = col0 + k;
+                const int pt = pt_base + sub * npt + k;
                 if (pt >= n_pts) break;
                 const float v = sv[cl * vstride + col];
                 const float gx = sg[cl * gstride + 3 * col], gy = sg[cl * gstride + 3 * col + 1],
@@ -1555,7 +1572,7 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
                 }
             }
         }
-        __syncwarp();
+        if constexpr (kCoop) __syncthreads(); else __syncwarp();
     }
 }
 
