@@ -7,8 +7,10 @@ OUT=gpurun_out/r02d_n$N
 mkdir -p "$OUT"
 export NCCL_DEBUG=WARN
 if [ "$N" = "2" ]; then
-  nvcc -O3 -gencode arch=compute_100a,code=sm_100a scripts/ubench_peer_store.cu -o /tmp/ubench_peer_store 2> "$OUT/ubench_build.err" && /tmp/ubench_peer_store > "$OUT/ubench_peer_store.jsonl" 2>&1
-  cat "$OUT/ubench_peer_store.jsonl"
+  timeout 600 python -m pytest tests/test_gpu_composed.py -m gpu -x -q > "$OUT/pytest_composed.log" 2>&1; echo "pytest rc=$?" >> "$OUT/pytest_composed.log"
+  tail -3 "$OUT/pytest_composed.log"
+
+
   timeout 600 python -m pytest tests/test_gpu_peer.py -m gpu -x -q > "$OUT/pytest_peer.log" 2>&1; echo "pytest rc=$?" >> "$OUT/pytest_peer.log"
   tail -5 "$OUT/pytest_peer.log"
 fi
