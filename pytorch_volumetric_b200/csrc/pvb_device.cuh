@@ -617,4 +617,44 @@ __device__ __forceinline__ void composed_consider(const pvb_sdf_desc &d, const N
     }
 }
 
+// ----------------------------------------------------------------------------
+// Index arithmetic of robot_serial_kernel (pvb_kernels.cu), kept here so that the CPU tier can check it exhaustively
+// (tests/test_hostsim.py): which configurations a tile holds, and which 16-byte piece of a staging tile a thread flushes.
+
+// Configuration tiles.  The first cfg_count / 32 tiles hold 32 configurations each (lanes = configurations, one point
+// per warp step).  The remainder R = cfg_count % 32 is split by its binary digits into FULL tiles of 16 / 8 / 4 / 2 / 1
+// configurations, in which the 32 lanes are 32 / LC point groups x LC configurations: no lane ever idles because the
+// configuration count is not a multiple of 32 (200 = 6 x 32 + 8 ran a seventh tile at 8 of 32 lanes: 11 % of the time;
+// the 25-configuration slab of an 8-GPU split ran at 25 of 32).
+__device__ __forceinline__ void rs_tile(int cfg_count, int t, int &c0, int &lc_log2) {
+    const int n_full = cfg_count >> 5;
+    if (t < n_full) { c0 = t << 5; lc_log2 = 5; return; }
+    int rem = cfg_count & 31, idx = t - n_full;
+    c0 = n_full << 5;
+    lc_log2 = 0;
+    for (int b = 4; b >= 0; --b) {
+        if (rem & (1 << b)) {
+            if (idx == 0) { lc_log2 = b; return; }
+            --idx;
+            c0 += 1 << b;
+        }
+    }
+}
+
+// A staging tile holds LC = 32 >> sub_log2 configuration rows of row_pts = (1 << (w_log2 + chunk_log2 + sub_log2)) points:
+// row_pts values and 3 row_pts gradient floats per row.  It leaves as LC * row_pts pieces of 16 bytes -- the first
+// LC * row_pts / 4 are values, the rest gradients -- numbered so that consecutive pieces are consecutive in a row.
+// Piece c -> (values or gradients, row, index of the piece inside the row's values / gradients).
+__device__ __forceinline__ void rs_flush_piece(int c, int chunk_log2, int sub_log2, int w_log2, bool &is_val, int &row,
+                                               int &part) {
+    const int vper_log2 = w_log2 + chunk_log2 - 2 + sub_log2;    // value pieces per row = row_pts / 4
+    const int gunit = 3 << (w_log2 + chunk_log2 - 2);            // gradient pieces per row and point group
+    const int gper = gunit << sub_log2;                          // gradient pieces per row = 3 row_pts / 4
+    const int n_val = 8 << (w_log2 + chunk_log2);                // value pieces of the tile = LC * row_pts / 4
+    is_val = c < n_val;
+    const int g = is_val ? c : c - n_val;
+    row = is_val ? g >> vper_log2 : (g >> sub_log2) / gunit;
+    part = is_val ? g & ((1 << vper_log2) - 1) : g - row * gper;
+}
+
 }  // namespace pvb

@@ -1358,26 +1358,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) {      // one MUFU.RSQ, n
     return r;
 }
 
-// Configuration tiles.  The first cfg_count / 32 tiles hold 32 configurations each (lanes = configurations, one point
-// per warp step).  The remainder R = cfg_count % 32 is split by its binary digits into FULL tiles of 16 / 8 / 4 / 2 / 1
-// configurations, in which the 32 lanes are 32 / LC point groups x LC configurations: no lane ever idles because the
-// configuration count is not a multiple of 32 (200 = 6 x 32 + 8 ran a seventh tile at 8 of 32 lanes: 11 % of the time;
-// the 25-configuration slab of an 8-GPU split ran at 25 of 32).
-__device__ __forceinline__ void rs_tile(int cfg_count, int t, int &c0, int &lc_log2) {
-    const int n_full = cfg_count >> 5;
-    if (t < n_full) { c0 = t << 5; lc_log2 = 5; return; }
-    int rem = cfg_count & 31, idx = t - n_full;
-    c0 = n_full << 5;
-    lc_log2 = 0;
-    for (int b = 4; b >= 0; --b) {
-        if (rem & (1 << b)) {
-            if (idx == 0) { lc_log2 = b; return; }
-            --idx;
-            c0 += 1 << b;
-        }
-    }
-}
-
+// (configuration tiles and the flush index arithmetic: rs_tile / rs_flush_piece in pvb_device.cuh, checked on the CPU tier)
 template <int kDest>
 __global__ void __launch_bounds__(kRbCfg * kRsWarps, PVB_RS_MINB)
 robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, const float *__restrict__ xforms,
@@ -1521,19 +1502,13 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
         if (vec && full) {
             // LC * row_pts pieces of 16 B per tile: the first quarter values, the rest gradients; the tile's threads take
             // consecutive pieces (one row segment per warp instruction), npt pieces each
-            const int vper_log2 = w_log2 + chunk_log2 - 2 + sub_log2;    // value pieces per row = row_pts / 4
-            const int gunit = 3 << (w_log2 + chunk_log2 - 2);            // gradient pieces per row and point group
-            const int gper = gunit << sub_log2;
-            const int n_val = 8 << (w_log2 + chunk_log2);                // value pieces of the tile = LC * row_pts / 4
             const int me = kCoop ? (int)threadIdx.x : lane;
             constexpr int kGroup = kCoop ? kRbCfg * kRsWarps : 32;
 #pragma unroll 1
             for (int j = 0; j < npt; ++j) {
-                const int c = me + kGroup * j;
-                const bool is_val = c < n_val;
-                const int g = is_val ? c : c - n_val;
-                const int row = is_val ? g >> vper_log2 : (g >> sub_log2) / gunit;
-                const int part = is_val ? g & ((1 << vper_log2) - 1) : g - row * gper;
+                bool is_val;
+                int row, part;
+                rs_flush_piece(me + kGroup * j, chunk_log2, sub_log2, w_log2, is_val, row, part);
                 const float *src = is_val ? sv + row * vstride + 4 * part : sg + row * gstride + 4 * part;
                 const float4 v4 = make_float4(src[0], src[1], src[2], src[3]);
                 const size_t o_row = (size_t)(c0 + row) * n_pts + tile_base;

@@ -113,3 +113,11 @@ extern "C" void sim_sphere(float radius, const float *pts, long long n, float *v
 }
 
 extern "C" float sim_hash_normal(uint32_t seed, unsigned long long idx, uint32_t comp) { return hash_normal(seed, idx, comp); }
+
+// index arithmetic of robot_serial_kernel
+extern "C" void sim_rs_tile(int cfg_count, int t, int *c0, int *lc_log2) { rs_tile(cfg_count, t, *c0, *lc_log2); }
+extern "C" void sim_rs_flush_piece(int c, int chunk_log2, int sub_log2, int w_log2, int *is_val, int *row, int *part) {
+    bool v;
+    rs_flush_piece(c, chunk_log2, sub_log2, w_log2, v, *row, *part);
+    *is_val = v ? 1 : 0;
+}

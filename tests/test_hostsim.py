@@ -383,3 +383,43 @@ def test_axis_parity_fuzz_on_perturbed_closed_meshes(built_lib):
         assert np.array_equal(px[m], (votes[m] == 3).astype(np.int32)), it
         checked += int(m.sum())
     assert checked > 10_000
+
+
+def test_robot_serial_tiles_and_flush_pieces_cover_everything_once(built_lib):
+    """Index arithmetic of robot_serial_kernel (pvb_device.cuh rs_tile / rs_flush_piece): for every configuration count
+    the tiles are full, disjoint and cover [0, cfg_count); for every tile shape (LC = 32..1), step size (4 / 8 points) and
+    flush mode (per warp / per block) the 16-byte pieces cover every value and gradient float of the tile exactly once,
+    consecutive pieces are consecutive in memory, and every piece is 16-byte aligned in the output."""
+    import ctypes
+    L = hs.lib()
+    for cfg_count in list(range(1, 300)) + [1000, 4097]:
+        seen = np.zeros(cfg_count, dtype=np.int32)
+        n_tiles = (cfg_count >> 5) + bin(cfg_count & 31).count("1")
+        for t in range(n_tiles):
+            c0, lc = ctypes.c_int(), ctypes.c_int()
+            L.sim_rs_tile(cfg_count, t, ctypes.byref(c0), ctypes.byref(lc))
+            assert 0 <= lc.value <= 5 and c0.value % (1 << lc.value) == 0
+            seen[c0.value:c0.value + (1 << lc.value)] += 1
+        assert (seen == 1).all(), cfg_count
+    for w_log2 in (0, 3):
+        for chunk_log2 in (2, 3):
+            for sub_log2 in range(6):
+                LC = 32 >> sub_log2
+                row_pts = 1 << (w_log2 + chunk_log2 + sub_log2)
+                n_pieces = LC * row_pts
+                val = np.zeros((LC, row_pts), dtype=np.int32)
+                grad = np.zeros((LC, 3 * row_pts), dtype=np.int32)
+                prev = None
+                for c in range(n_pieces):
+                    iv, row, part = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+                    L.sim_rs_flush_piece(c, chunk_log2, sub_log2, w_log2, ctypes.byref(iv), ctypes.byref(row), ctypes.byref(part))
+                    assert 0 <= row.value < LC
+                    if iv.value:
+                        val[row.value, 4 * part.value:4 * part.value + 4] += 1
+                    else:
+                        grad[row.value, 4 * part.value:4 * part.value + 4] += 1
+                    cur = (iv.value, row.value, part.value)
+                    if prev is not None and prev[0] == cur[0] and prev[1] == cur[1]:
+                        assert cur[2] == prev[2] + 1            # consecutive pieces are neighbours in the row
+                    prev = cur
+                assert (val == 1).all() and (grad == 1).all(), (w_log2, chunk_log2, sub_log2)
