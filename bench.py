@@ -474,6 +474,7 @@ class C3(Workload):
                      "l2_policy": "6 rotating device copies of the point set (144 MB > L2); results are fresh buffers"}
         if cached:
             self.kernel = "composed_query_kernel<false>"
+            self.name = "c3cached"          # its own entry in profiles/ncu_traffic.json
 
     def step(self, i):
         return self.comp(self.copies[i % len(self.copies)])
