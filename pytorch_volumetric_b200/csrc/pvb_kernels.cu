@@ -2343,7 +2343,8 @@ static int composed_dispatch(const pvb_sdf_desc *descs, int32_t n_sdf, int32_t n
     // the point-serial kernel has no fill problem (remainder configurations run in lane-split tiles): any batch of
     // PVB_ROBOT_MIN_CFG or more configurations takes it
     static const int serial_min_cfg = [] { const char *e = getenv("PVB_ROBOT_MIN_CFG"); return e ? atoi(e) : 8; }();
-    const bool serial_ok = robot_kernel >= 2 && n_sdf <= kRsMaxS && cfg_count >= serial_min_cfg;
+    const bool serial_ok = robot_kernel >= 2 && n_sdf <= kRsMaxS && cfg_count >= serial_min_cfg &&
+                           cfg_count <= 65535 * kRbCfg;          // one grid row per 32-configuration tile
     if (robot_kernel && cfg_major && all_grid && (rb_filled || serial_ok)) {
         const int vec_rows = (tg ? tg->vec : (out_aligned && (n_pts % 4 == 0))) && aligned16(pts);
         // PVB_ROBOT_KERNEL: 2 (default) = point-serial nearest-sphere-first kernel for <= 8 links, 1 = the
