@@ -716,7 +716,8 @@ __global__ void __launch_bounds__(kCompThreads, (kMesh ? PVB_COMPMESH_MINB : (PT
 composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, const float *__restrict__ xforms,
                       int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, long long first_pt,
                       long long n_pts, uint32_t mesh_mode, float *__restrict__ out_val, float *__restrict__ out_grad,
-                      int *__restrict__ out_which, const __grid_constant__ OutTargets tg) {
+                      int *__restrict__ out_which, const __grid_constant__ OutTargets tg, int nearest_first,
+                      float margin_max) {
     __shared__ __align__(16) float s_xf[kCompSmemXf][12];
     const bool use_smem = n_sdf <= kCompSmemXf;
     NodeStage st; st.smem = nullptr; st.n = 0;
@@ -766,7 +767,53 @@ composed_query_kernel(const __grid_constant__ DescPack<MAXS> descs, int n_sdf, c
             // pvb_device.cuh).  (Evaluating the sub-SDF with the smallest AABB lower bound first -- an extra pass
             // over all of them without table access -- saves lookups but measured 1.8x slower: the kernel is
             // issue-bound; profiles/README.md.)
-            for (int si = 0; si < n_sdf; ++si) {
+            // ... except when sub-SDFs are MESHES (kMesh, one point per thread): an evaluation is a tree walk of
+            // thousands of instructions, so one cheap pass computes every sub-SDF's AABB lower bound and the thread
+            // then evaluates them NEAREST BOUND FIRST, stopping as soon as the smallest remaining bound exceeds the
+            // running minimum.  A fixed order evaluates every sub-SDF that is a running record when its turn comes
+            // (~H_16 = 3.4 of 16 at C3, plus those inside the slack); nearest-first evaluates the winner and its near
+            // ties.  Exact for the same reason as the fixed order: bounds are conservative and the argmin keeps
+            // torch's first-index rule explicitly.
+            bool ordered = false;
+            if constexpr (kMesh && PTS == 1) {
+                if (n_sdf <= 32 && nearest_first) {
+                    ordered = true;
+                    float key[32];                           // squared lower bound; -1 = no valid bound (evaluate)
+                    unsigned todo = n_sdf >= 32 ? 0xffffffffu : ((1u << n_sdf) - 1u);
+                    for (int s = 0; s < n_sdf; ++s) {
+                        const pvb_sdf_desc &d = descs.d[s];
+                        float4 r0, r1, r2;
+                        load_xf(s, r0, r1, r2);
+                        const bool bounded = d.kind == PVB_KIND_GRID ? (d.flags & PVB_GRID_PRUNE_OK) != 0
+                                             : (d.kind == PVB_KIND_MESH && (d.flags & PVB_MESH_CLOSED) && (mesh_mode & PVB_MESH_SIGNED));
+                        key[s] = bounded ? composed_aabb_lb2(d, composed_xform(r0, r1, r2, p[0])) : -1.f;
+                    }
+                    while (todo) {
+                        int s = -1;
+                        float kmin = PVB_INF;
+                        for (int t = 0; t < n_sdf; ++t)
+                            if ((todo >> t) & 1u) { if (key[t] < kmin) { kmin = key[t]; s = t; } }
+                        if (s < 0) break;
+                        todo &= ~(1u << s);
+                        const pvb_sdf_desc &d = descs.d[s];
+                        if (bs[0] >= 0 && kmin >= 0.f) {
+                            // every remaining bound is at least kmin: when even the most generous margin cannot bring
+                            // it under the running minimum, nothing left can win (margins are per sub-SDF: test this one
+                            // exactly, and stop the loop only on the margin-free comparison)
+                            const float thr = best[0] + d.prune_margin;
+                            if (thr < 0.f || kmin > thr * thr) {
+                                if (best[0] + margin_max < 0.f || kmin > (best[0] + margin_max) * (best[0] + margin_max)) break;
+                                continue;
+                            }
+                        }
+                        float4 r0, r1, r2;
+                        load_xf(s, r0, r1, r2);
+                        const uint64_t idx = ((uint64_t)cfg * (uint64_t)n_pts + (uint64_t)i0) * (uint64_t)n_sdf + (uint64_t)s;
+                        composed_consider<kMesh>(d, st, s, composed_xform(r0, r1, r2, p[0]), mesh_mode, idx, best[0], bg[0], bs[0]);
+                    }
+                }
+            }
+            for (int si = 0; si < (ordered ? 0 : n_sdf); ++si) {
                 const int s = descs.order[si];
                 const pvb_sdf_desc &d = descs.d[s];
                 float4 r0, r1, r2;
@@ -2171,15 +2218,19 @@ static int launch_composed(const pvb_sdf_desc *descs, int n_sdf, const float *xf
     const long long cap = (long long)sm_count() * 64;     // bound the block count for huge configuration batches
     if ((long long)gx * gy > cap) { gy = (int)(cap / gx); if (gy < 1) gy = 1; }
     dim3 grid((unsigned)gx, (unsigned)gy);
+    // mesh sub-SDFs: nearest-bound-first evaluation (PVB_COMP_NEAREST_FIRST=0 restores the fixed bit-reversed order)
+    static const int nearest_first = [] { const char *e = getenv("PVB_COMP_NEAREST_FIRST"); return e ? atoi(e) : 1; }();
+    float margin_max = 0.f;
+    for (int i = 0; i < n_sdf; ++i) margin_max = descs[i].prune_margin > margin_max ? descs[i].prune_margin : margin_max;
     timing_mark(0, stream);
     if (tg)
         composed_query_kernel<kMesh, PTS, MAXS, true><<<grid, kCompThreads, 0, stream>>>(
             pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, first_pt, n_pts, mesh_mode, nullptr, nullptr,
-            out_which, *tg);
+            out_which, *tg, nearest_first, margin_max);
     else
         composed_query_kernel<kMesh, PTS, MAXS, false><<<grid, kCompThreads, 0, stream>>>(
             pack, n_sdf, xforms, n_cfg, cfg_begin, cfg_count, pts, first_pt, n_pts, mesh_mode, out_val, out_grad,
-            out_which, OutTargets{});
+            out_which, OutTargets{}, nearest_first, margin_max);
     timing_mark(1, stream);
     PVB_CHECK_LAUNCH("pvb_composed_query");
     return PVB_OK;
