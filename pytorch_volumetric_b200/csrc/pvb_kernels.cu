@@ -170,8 +170,18 @@ __device__ __forceinline__ f3 load_point(const float *__restrict__ pts, long lon
 // batches are therefore binned into 64^3 Morton-ordered cells over the padded mesh AABB with a counting sort
 // (histogram by atomics, single-block scan, scatter) and the tree walk processes them in that order through an
 // index permutation; results are written to the original slots, so callers see no reordering.
-constexpr int kSortBits = 6;                               // per axis
+constexpr int kSortBits = 6;                               // per axis: 64^3 cells (default)
 constexpr int kSortCells = 1 << (3 * kSortBits);           // 262144
+constexpr int kSortBitsMax = 8;                            // 256^3 cells = 64 MB of counters
+
+// Cells per axis for a batch of n queries.  Lanes of a warp are 32 consecutive queries of the binned order: they walk
+// the same part of the tree only if a cell is not much larger than the triangles around it, and a cell holds n / cells
+// queries in arbitrary order.  PVB_SORT_BITS overrides (measurements in profiles/README.md).
+static int sort_bits_for(long long n) {
+    static const int forced = [] { const char *e = getenv("PVB_SORT_BITS"); return e ? atoi(e) : 0; }();
+    if (forced >= 4 && forced <= kSortBitsMax) return forced;
+    return n >= (1ll << 21) ? 7 : kSortBits;
+}
 constexpr long long kSortMinPoints = 1 << 15;
 
 __device__ __forceinline__ uint32_t part1by2(uint32_t x) {  // spread the low 10 bits, two zeros between bits
@@ -187,6 +197,7 @@ struct SortFrame {           // cell = morton(quantise(((M p) - lo) * scale)); M
     float lo[3], scale[3];
     float xf[12];
     int use_xf;
+    int bits;                // cells per axis = 1 << bits
 };
 
 __device__ __forceinline__ uint32_t sort_cell(const SortFrame &f, f3 p) {
@@ -194,7 +205,7 @@ __device__ __forceinline__ uint32_t sort_cell(const SortFrame &f, f3 p) {
         p = mk3(fmaf(f.xf[0], p.x, fmaf(f.xf[1], p.y, fmaf(f.xf[2], p.z, f.xf[3]))),
                 fmaf(f.xf[4], p.x, fmaf(f.xf[5], p.y, fmaf(f.xf[6], p.z, f.xf[7]))),
                 fmaf(f.xf[8], p.x, fmaf(f.xf[9], p.y, fmaf(f.xf[10], p.z, f.xf[11]))));
-    const float m = (float)((1 << kSortBits) - 1);
+    const float m = (float)((1 << f.bits) - 1);
     const uint32_t cx = (uint32_t)fminf(fmaxf((p.x - f.lo[0]) * f.scale[0], 0.f), m);   // NaN -> 0
     const uint32_t cy = (uint32_t)fminf(fmaxf((p.y - f.lo[1]) * f.scale[1], 0.f), m);
     const uint32_t cz = (uint32_t)fminf(fmaxf((p.z - f.lo[2]) * f.scale[2], 0.f), m);
@@ -218,9 +229,9 @@ __global__ void sort_hist_kernel(const SortFrame f, const float *__restrict__ pt
 
 // exclusive scan of kSortCells counters in place, one block of 1024 threads (256 counters per thread, moved as
 // 64 independent 128-bit loads so that the single block is not serialised on L2 latency: 442 us -> tens of us)
-__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t *__restrict__ hist) {
+__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t *__restrict__ hist, int n_cells) {
     __shared__ uint32_t warp_sum[32];
-    constexpr int per4 = kSortCells / 1024 / 4;       // uint4 per thread
+    const int per4 = n_cells / 1024 / 4;              // uint4 per thread (n_cells is a power of two >= 4096)
     uint4 *mine = reinterpret_cast<uint4 *>(hist) + (size_t)threadIdx.x * per4;
     uint32_t s = 0;
 #pragma unroll 16
@@ -294,7 +305,7 @@ struct SortedQueries {
 static size_t sort_workspace_bytes(long long n) {
     // counters | cell id / inverse permutation | binned points | result staging, each 16-byte aligned
     const size_t n4 = ((size_t)n * 4 + 15) / 16 * 16;
-    return (size_t)kSortCells * 4 + n4 + (size_t)n * 16 * 2;
+    return ((size_t)4 << (3 * sort_bits_for(n))) + n4 + (size_t)n * 16 * 2;
 }
 
 // ================================================================ mesh query
@@ -2028,27 +2039,32 @@ static SortedQueries sort_queries(const pvb_sdf_desc *obj, const float *pts, lon
         workspace_bytes < sort_workspace_bytes(n))
         return sq;
     uint32_t *hist = reinterpret_cast<uint32_t *>(workspace);
-    uint32_t *cell = hist + kSortCells;
+    const int bits = sort_bits_for(n);
+    const size_t n_cells = (size_t)1 << (3 * bits);
+    uint32_t *cell = hist + n_cells;
     const size_t n4 = ((size_t)n * 4 + 15) / 16 * 16;
     float4 *sorted = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(cell) + n4);
     float4 *stage = sorted + n;
     SortFrame f;
     for (int a = 0; a < 3; ++a) {
         const float ext = obj->bb_max[a] - obj->bb_min[a];
-        const float pad = 0.5f * ext + 1e-6f;                 // queries beyond the padded box clamp to the border cells
+        // queries beyond the padded box clamp to the border cells.  Mesh queries may lie anywhere around the object
+        // (pad = half its extent); a chamfer cloud hugs the surface (xf_dev given): a tenth keeps the cells 1.7x finer
+        const float pad = (xf_dev ? 0.1f : 0.5f) * ext + 1e-6f;
         f.lo[a] = obj->bb_min[a] - pad;
-        f.scale[a] = (float)(1 << kSortBits) / (ext + 2.f * pad);
+        f.scale[a] = (float)(1 << bits) / (ext + 2.f * pad);
     }
     f.use_xf = xf_dev != nullptr;
+    f.bits = bits;
     for (int e = 0; e < 12; ++e) f.xf[e] = 0.f;
-    if (cudaMemsetAsync(hist, 0, (size_t)kSortCells * 4, stream) != cudaSuccess) {
+    if (cudaMemsetAsync(hist, 0, n_cells * 4, stream) != cudaSuccess) {
         pvb_set_error("sort_queries: cudaMemsetAsync failed");
         *rc = PVB_ERR_CUDA;
         return sq;
     }
     const int blocks = grid_for(n, 256, 8);
     sort_hist_kernel<<<blocks, 256, 0, stream>>>(f, pts, n, xf_dev, cell, hist);
-    sort_scan_kernel<<<1, 1024, 0, stream>>>(hist);
+    sort_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int)n_cells);
     sort_scatter_kernel<<<blocks, 256, 0, stream>>>(cell, pts, n, hist, sorted);
     if (cudaGetLastError() != cudaSuccess) {
         pvb_set_error("sort_queries: launch failed");

@@ -121,3 +121,21 @@ extern "C" void sim_rs_flush_piece(int c, int chunk_log2, int sub_log2, int w_lo
     rs_flush_piece(c, chunk_log2, sub_log2, w_log2, v, *row, *part);
     *is_val = v ? 1 : 0;
 }
+
+// closest-point walk with a per-query initial search radius (squared): how many node visits / triangle tests are
+// irreducible once the answer is known (scripts/traversal_stats.py, the lower bound any seeding scheme could reach)
+extern "C" void sim_closest_seeded(const pvb_sdf_desc *m, const float *pts, long long n, const float *init_d2,
+                                   long long *stats_out) {
+    NodeStage st; st.smem = nullptr; st.n = 0;
+    long long a = 0, b = 0;
+#pragma omp parallel reduction(+ : a, b)
+    {
+        t_stats = SimStats{0, 0, 0, 0};
+#pragma omp for schedule(dynamic, 256)
+        for (long long i = 0; i < n; ++i)
+            (void)bvh_closest(reinterpret_cast<const float4 *>(m->nodes), st, reinterpret_cast<const float4 *>(m->tris),
+                              point(pts, i), init_d2 ? init_d2[i] : PVB_INF);
+        a += t_stats.closest_nodes; b += t_stats.closest_tris;
+    }
+    stats_out[0] = a; stats_out[1] = b;
+}
