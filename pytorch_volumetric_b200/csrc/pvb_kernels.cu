@@ -180,7 +180,10 @@ constexpr int kSortBitsMax = 8;                            // 256^3 cells = 64 M
 static int sort_bits_for(long long n) {
     static const int forced = [] { const char *e = getenv("PVB_SORT_BITS"); return e ? atoi(e) : 0; }();
     if (forced >= 4 && forced <= kSortBitsMax) return forced;
-    return n >= (1ll << 21) ? 7 : kSortBits;
+    // measured (profiles/r02/tune_sort_bits.jsonl, ms per step at 6 / 7 / 8 bits): mesh10k 7.66 / 7.96 / 14.4, C5 6.77 /
+    // 6.74 / 13.1, mesh50k 17.5 / 16.8 / 23.4 -- finer cells do not pay for the larger histogram; 64^3 stays
+    (void)n;
+    return kSortBits;
 }
 constexpr long long kSortMinPoints = 1 << 15;
 
