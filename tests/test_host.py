@@ -420,3 +420,16 @@ def test_grid_descriptor_from_reference_table_without_gpu():
             assert d.bb_min[k] == np.float32(z["bb"][k, 0]) and d.bb_max[k] == np.float32(z["bb"][k, 1])
         want = S.grid_prune_margin(val, [r[0] for r in ranges], [r[1] for r in ranges], z["bb"].astype(np.float32))
         assert abs(d.prune_margin - want) < 1e-7
+
+
+def test_cpulist_parser_and_numa_binding_is_a_noop_without_gpu():
+    from pytorch_volumetric_b200 import distributed as pd
+    assert pd._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert pd._parse_cpulist("") == set()
+    assert pd._parse_cpulist("5") == {5}
+    # no GPU here: nothing is known about the PCIe root, and the affinity is left alone
+    before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    assert pd.gpu_numa_node(0) is None
+    assert pd.bind_to_gpu_numa_node(0) is None
+    if before is not None:
+        assert os.sched_getaffinity(0) == before
