@@ -647,14 +647,14 @@ __device__ __forceinline__ void rs_tile(int cfg_count, int t, int &c0, int &lc_l
 // Piece c -> (values or gradients, row, index of the piece inside the row's values / gradients).
 __device__ __forceinline__ void rs_flush_piece(int c, int chunk_log2, int sub_log2, int w_log2, bool &is_val, int &row,
                                                int &part) {
-    const int vper_log2 = w_log2 + chunk_log2 - 2 + sub_log2;    // value pieces per row = row_pts / 4
-    const int gunit = 3 << (w_log2 + chunk_log2 - 2);            // gradient pieces per row and point group
-    const int gper = gunit << sub_log2;                          // gradient pieces per row = 3 row_pts / 4
-    const int n_val = 8 << (w_log2 + chunk_log2);                // value pieces of the tile = LC * row_pts / 4
+    const int vper_log2 = w_log2 + chunk_log2 - 2 + sub_log2;    // value pieces per row = row_pts / 4 (a power of two)
+    const int n_val = 32 << (w_log2 + chunk_log2 - 2);           // value pieces of the tile = LC * row_pts / 4
     is_val = c < n_val;
     const int g = is_val ? c : c - n_val;
-    row = is_val ? g >> vper_log2 : (g >> sub_log2) / gunit;
-    part = is_val ? g & ((1 << vper_log2) - 1) : g - row * gper;
+    const int q = g >> vper_log2;                                // values: the row; gradients (3 x as many per row): 3 row + k
+    // q / 3 without a division: q < 3 * 32, and (q * 43691) >> 17 == q / 3 for every q < 98304
+    row = is_val ? q : (q * 43691) >> 17;
+    part = is_val ? g & ((1 << vper_log2) - 1) : g - ((3 * row) << vper_log2);
 }
 
 }  // namespace pvb

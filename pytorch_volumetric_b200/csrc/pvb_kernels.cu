@@ -1383,8 +1383,9 @@ robot_query_kernel(const __grid_constant__ RobotPack<MAXS> pk, int n_sdf, const 
 // warp pay; 17 % in the bounding-sphere tests of all 8 links x 4 points; L1 wavefronts at 51 % (16-byte stores to 32
 // different rows per instruction); 80 registers, 33 % warps active, long-scoreboard (gather latency) the top stall.
 //   * one point at a time per warp (lanes = 32 configurations), so the state of a point is 8 registers, not 32;
-//   * the lane's 8 bounding spheres live in REGISTERS for the whole kernel (they were 4 LDS wavefronts per link and
-//     point); per point one pass turns them into lower bounds lb_s <= value_s, kept in 8 registers;
+//   * the (configuration, link) bounding spheres sit in shared memory, one LDS.128 per link and point (keeping them in
+//     32 registers was measured slower, see below); per point one pass turns them into lower bounds lb_s <= value_s,
+//     kept in 8 registers;
 //   * the link with the smallest bound (lane 0's, shuffled: neighbouring configurations agree) is visited FIRST, so
 //     the running minimum is tight at once and `lb_s > best` (one compare) rejects most other links for most lanes;
 //     ties keep torch.argmin's first-index rule explicitly, so the order never changes a result;
@@ -1392,6 +1393,12 @@ robot_query_kernel(const __grid_constant__ RobotPack<MAXS> pk, int n_sdf, const 
 //     values + 96 B of gradients per configuration row), one 16-byte store per lane and destination -- local
 //     buffer, peer buffers or multicast -- with __syncwarp only: no block barrier anywhere in the loop.
 // Pruning stays exact (bounds are conservative), arithmetic of a visit is unchanged: bit-identical to the other kernels.
+// Instruction diet (profiles/r02/c4_serial_diet_lines.txt, tune_c4_diet.jsonl): the nearest sphere from a 5-instruction
+// min over keys that carry the link index in their low mantissa bits (was compare + select per link), no per-link tests
+// of `point exists` / `si < n_sdf` (slots beyond n_sdf carry a +inf bound), a division-free flush index and per-lane
+// staging pointers: 640 -> 557 warp instructions per (point, 32 configurations), 0.508 -> 0.474 ms on C4.  What bounds
+// it now: L1 data-pipe wavefronts at 78 % (~166 per point: 32 sphere reads, ~54 transform rows, ~66 table gathers of 32
+// distinct sectors, 12 staging) with the issue slots at 70 %.
 constexpr int kRsWarps = 8;
 constexpr int kRsChunk = 8;                       // consecutive points per warp between two flushes
 constexpr int kRsMaxS = 8;
@@ -1412,6 +1419,16 @@ struct __align__(16) RsSmem {
     float sv[kRsWarps][kRbCfg][kRsValStride];
     float sg[kRsWarps][kRbCfg][kRsGradStride];
 };
+
+// sqrt(0.9998) * 0.999999: 0.9998 on the squared distance absorbs the 1e-5 non-rigidity tolerated below, 0.999999 the
+// approximate reciprocal square root (2 ulp) and the roundings of the three fused multiply-adds
+constexpr float kRsBoundScale = 0.99989899f;
+
+__device__ __forceinline__ int and_or(int a, int b, int c) {   // (a & b) | c
+    int r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 
 __device__ __forceinline__ float rsqrt_approx(float x) {      // one MUFU.RSQ, no denormal fix-up (callers keep x >= 1e-20)
     float r;
@@ -1456,7 +1473,8 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
     // ---- bounding spheres (object frame) of every (configuration, link) of the tile ----
     for (int item = threadIdx.x; item < LC * kRsMaxS; item += blockDim.x) {
         const int ci = item & (LC - 1), si = item >> lc_log2;
-        float4 sp = make_float4(0.f, 0.f, 0.f, PVB_INF);
+        // slots beyond n_sdf: radius -inf, so that their bound is +inf -- never the nearest, never visited
+        float4 sp = make_float4(0.f, 0.f, 0.f, -PVB_INF);
         if (si < n_sdf) {
             const pvb_sdf_desc &d = pk.d[si];
             const float4 r0 = sm.xf[ci][3 * si], r1 = sm.xf[ci][3 * si + 1], r2 = sm.xf[ci][3 * si + 2];
@@ -1495,6 +1513,9 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
     const int row_pts = pts_per_step << w_log2;                             // points per row of the tile
     const int vstride = row_pts + 1, gstride = 3 * row_pts + 1;             // odd: conflict-free STS.32 across lanes
     const int col0 = (kCoop ? warp * pts_per_step : 0) + sub * npt;         // this lane's first column
+    // ~7 in a register the compiler cannot fold (n_sdf <= 8): (bits & ~7) | si is then ONE LOP3 with the immediate si
+    const int low3_off = ~7 | (n_sdf >> 30);
+    float *const sv_lane = sv + cl * vstride + col0, *const sg_lane = sg + cl * gstride + 3 * col0;
     const int n_super = (n_chunks + kRsWarps - 1) / kRsWarps;
     for (int sup = blockIdx.x; sup < n_super; sup += gx_tile) {
         const int chunk = sup * kRsWarps + warp;
@@ -1512,18 +1533,22 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
             // 0.9998 absorbs the 1e-5 non-rigidity tolerated above, 0.999999 the approximate reciprocal square root
             // (2 ulp); + 1e-20 keeps its argument a normal number (and raises the bound by < 1e-10, inside the 1e-5
             // slack of the radius).  radius = inf (bound not valid) gives -inf: never rejected.
-            float lb[kRsMaxS];
-            float lb_min = PVB_INF;
-            int pred = 0;
+            float lb[kRsMaxS], key[kRsMaxS];
 #pragma unroll
             for (int si = 0; si < kRsMaxS; ++si) {
                 const float4 sp = sm.sph[cl][si];
                 const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
-                const float d2 = fmaf(dx * dx + dy * dy + dz * dz, 0.9998f, 1e-20f);
-                lb[si] = fmaf(d2 * rsqrt_approx(d2), 0.999999f, -sp.w);
-                if (si < n_sdf && lb[si] < lb_min) { lb_min = lb[si]; pred = si; }
+                const float d2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, 1e-20f)));
+                lb[si] = fmaf(d2 * rsqrt_approx(d2), kRsBoundScale, -sp.w);
+                // the link index rides in the 3 low mantissa bits: the smallest key names the nearest sphere
+                key[si] = __int_as_float(and_or(__float_as_int(lb[si]), low3_off, si));
             }
-            // one visiting order per point group: its first lane's nearest sphere (neighbouring configurations agree)
+            // one visiting order per point group: its first lane's nearest sphere (neighbouring configurations agree).
+            // Any link is a valid first visit -- the order never changes a result -- so the 7-ulp blur of the keys and
+            // fminf dropping the NaN patterns that +-inf bounds turn into do no harm; the clamp keeps it a real link.
+            const float kmin = fminf(fminf(fminf(key[0], key[1]), fminf(key[2], key[3])),
+                                     fminf(fminf(key[4], key[5]), fminf(key[6], key[7])));
+            int pred = min(__float_as_int(kmin) & 7, n_sdf - 1);
             pred = __shfl_sync(0xffffffffu, pred, sub << lc_log2);
             float best = PVB_INF;
             f3 bg = mk3(0.f, 0.f, 0.f);
@@ -1541,21 +1566,23 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
                     best = o.x; bg = mk3(o.y, o.z, o.w); bs = si;
                 }
             };
-            if (on) visit(pk.d[pred], pred);
+            // (lanes past the last point work on p = 0 and are not stored: no `on` in the conditions below)
+            visit(pk.d[pred], pred);
 #pragma unroll
             for (int si = 0; si < kRsMaxS; ++si) {
-                if (si < n_sdf) {
-                    // reject when the sphere bound already exceeds the running minimum (exact: lb <= value)
-                    if (on && si != pred && !(lb[si] > best)) visit(pk.d[si], si);
-                }
+                // reject when the sphere bound already exceeds the running minimum (exact: lb <= value); best is finite
+                // after the first visit, so the +inf bound of a slot beyond n_sdf never passes
+                if (si != pred && !(lb[si] > best)) visit(pk.d[si], si);
             }
+            // (Rotating the gradient inside the visit, while the rows are in registers, saves these 3 LDS.128 -- 12 of the
+            // ~166 L1 wavefronts a point costs -- but runs the 9 multiply-adds once per visit instead of once per point:
+            // 0.485 ms against 0.474 ms on C4; with 80 registers / 3 blocks per SM 0.519 ms.  profiles/r02/tune_c4_rot.jsonl)
             const int sb = max(bs, 0);
             const f3 go = composed_rotate_back(sm.xf[cl][3 * sb], sm.xf[cl][3 * sb + 1], sm.xf[cl][3 * sb + 2], bg);
-            const int col = col0 + k;
-            sv[cl * vstride + col] = best;
-            sg[cl * gstride + 3 * col] = go.x;
-            sg[cl * gstride + 3 * col + 1] = go.y;
-            sg[cl * gstride + 3 * col + 2] = go.z;
+            sv_lane[k] = best;
+            sg_lane[3 * k] = go.x;
+            sg_lane[3 * k + 1] = go.y;
+            sg_lane[3 * k + 2] = go.z;
             if (out_which && on) out_which[(size_t)(c0 + cl) * n_pts + pt] = bs;
         }
         if constexpr (kCoop) __syncthreads(); else __syncwarp();
