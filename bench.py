@@ -69,6 +69,16 @@ def ncu_traffic(workload):
     return None
 
 
+def ncu_limits(workload):
+    """Issue-slot / L1 data pipe / DRAM utilisation of the dominant kernel from the same committed capture: says what
+    bounds a kernel whose HBM fraction is small by nature (tree walks, the RobotSDF kernel)."""
+    path = os.path.join(ROOT, "profiles", "ncu_limits.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh).get(workload)
+    return None
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region through NVML (nvidia_ml_py).
 
@@ -755,7 +765,7 @@ def roofline_of(wl, kernel_ms):
     peak, peak_kind = measured_peaks()
     achieved = wl.alg_bytes / (kernel_ms * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": ncu_traffic(wl.name), "kernel": wl.kernel, "kernel_ms": kernel_ms,
+            "traffic": ncu_traffic(wl.name), "ncu": ncu_limits(wl.name), "kernel": wl.kernel, "kernel_ms": kernel_ms,
             "algorithmic_bytes_per_launch": wl.alg_bytes, "peak_source": f"of {peak_kind}"}
 
 
