@@ -135,6 +135,65 @@ def _winding_moments(nodes_u8, tris):
     return out
 
 
+class _HostChunkStream:
+    """Host batch in, pinned host results out, PCIe busy in both directions at once: chunk i is copied in on `s_in`
+    while chunk i-1 is computed on the current stream and chunk i-2 is copied out on `s_out`; two device slots per
+    direction, events order the reuse of a slot.  `tails` are the trailing shapes of the per-point outputs, e.g.
+    ((), (3,)) for value + gradient; `launch(d_in, m, d_outs)` enqueues the computation of one chunk of m points on
+    the current stream.
+
+    (Measured on the pool, CachedSDF, 1e7 points: one copy-in / launch / copy-out 5.1 ms, 2M-point chunks 3.7 ms, 4M
+    4.1 ms, 1M 11 ms -- small chunks are dominated by per-chunk stream/event bookkeeping on this host.)"""
+
+    def __init__(self, device, chunk, tails):
+        self.device, self.chunk, self.tails = device, chunk, tuple(tails)
+        with torch.cuda.device(device):
+            self.s_in, self.s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+            self.d_in = [torch.empty(chunk, 3, dtype=torch.float32, device=device) for _ in range(2)]
+            self.d_out = [[torch.empty(chunk, *t, dtype=torch.float32, device=device) for t in self.tails]
+                          for _ in range(2)]
+
+    def run(self, points, launch):
+        device, C = self.device, self.chunk
+        src = points.detach().reshape(-1, 3)
+        if src.dtype != torch.float32:
+            src = src.float()
+        src = src.contiguous()
+        n = src.shape[0]
+        with torch.cuda.device(device):
+            cur = torch.cuda.current_stream(device)
+            outs_h = [torch.empty(n, *t, dtype=torch.float32, pin_memory=True) for t in self.tails]
+            self.s_in.wait_stream(cur)
+            self.s_out.wait_stream(cur)
+            ev_comp = [None, None]      # computation finished reading d_in[b] / writing d_out[b]
+            ev_out = [None, None]       # copy-out finished reading d_out[b]
+            for i, lo in enumerate(range(0, n, C)):
+                hi = min(lo + C, n)
+                m = hi - lo
+                b = i & 1
+                with torch.cuda.stream(self.s_in):
+                    if ev_comp[b] is not None:
+                        self.s_in.wait_event(ev_comp[b])
+                    self.d_in[b][:m].copy_(src[lo:hi], non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(self.s_in)
+                cur.wait_event(ev_in)
+                if ev_out[b] is not None:
+                    cur.wait_event(ev_out[b])
+                launch(self.d_in[b], m, self.d_out[b])
+                ev_comp[b] = torch.cuda.Event()
+                ev_comp[b].record(cur)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(ev_comp[b])
+                    for h, d in zip(outs_h, self.d_out[b]):
+                        h[lo:hi].copy_(d[:m], non_blocking=True)
+                    ev_out[b] = torch.cuda.Event()
+                    ev_out[b].record(self.s_out)
+            self.s_out.synchronize()
+            cur.wait_stream(self.s_in)
+        return outs_h
+
+
 class ObjectFactory(abc.ABC):
     def __init__(self, name='', scale=1.0, vis_frame_pos=(0, 0, 0), vis_frame_rot=(0, 0, 0, 1),
                  plausible_suboptimality=0.001, mesh=None, ray_seed=0, **kwargs):
@@ -283,8 +342,15 @@ class ObjectFactory(abc.ABC):
         d.prune_margin = 1e-5 * max(1.0, float(np.abs(bb).max()))
 
     # -- the query (sdf.py:122-172) ----------------------------------------------
+    #: host batches at least this large are streamed through the GPU in chunks (_HostChunkStream); every chunk is
+    #: binned and walked on its own
+    host_pipeline_min_points = 1 << 22
+    host_pipeline_chunk = 1 << 21
+
     def _do_object_frame_closest_point(self, points_in_object_frame, compute_normal=False, device=None,
-                                       mode=nat.PVB_MESH_DEFAULT):
+                                       mode=nat.PVB_MESH_DEFAULT, want_closest=True):
+        """-> (closest | None, distance, gradient, normal | None); want_closest=False (MeshSDF.__call__ needs distance
+        and gradient only) skips the closest-point output and its copy to the host."""
         if torch.is_tensor(points_in_object_frame):
             dtype = points_in_object_frame.dtype
             out_device = points_in_object_frame.device
@@ -296,31 +362,65 @@ class ObjectFactory(abc.ABC):
             out_device = torch.device("cpu")
         lead = tuple(points_in_object_frame.shape[:-1])
         device = nat.compute_device(device)
+        if self.sign_mode not in ("parity", "winding"):
+            raise ValueError(f"sign_mode must be 'parity' or 'winding', got {self.sign_mode!r}")
+        winding = self.sign_mode == "winding" and bool(mode & nat.PVB_MESH_SIGNED)
+        L = nat.lib()
+        if (torch.is_tensor(points_in_object_frame) and out_device.type == "cpu" and dtype == torch.float32
+                and not winding and points_in_object_frame.shape[-1] == 3
+                and points_in_object_frame.numel() // 3 >= self.host_pipeline_min_points
+                and (self.axis_ray_when_closed and self.is_closed or not (mode & nat.PVB_MESH_SIGNED))):
+            # large host batch: copy-in / tree walk / copy-out overlapped chunk by chunk.  (Only where the sign test is
+            # the exact axis-aligned walk: the jittered diagonal ray of open meshes is seeded by the point's index in
+            # the call, so chunking would change which ray a point gets.)
+            tails = ((3,),) * bool(want_closest) + ((), (3,)) + ((3,),) * bool(compute_normal)
+            key = (device, self.host_pipeline_chunk, tails)
+            st = getattr(self, "_pipe_state", None)
+            if st is None or st[0] != key:
+                with torch.cuda.device(device):
+                    st = self._pipe_state = (key, _HostChunkStream(device, self.host_pipeline_chunk, tails),
+                                             nat.query_workspace(self.host_pipeline_chunk, device))
+            desc = self.native_desc(device)
+            ws = st[2]
+
+            def launch(d_in, m, d_out):
+                o = list(d_out)
+                closest = o.pop(0) if want_closest else None
+                dist, grad = o.pop(0), o.pop(0)
+                normal = o.pop(0) if compute_normal else None
+                nat.check(L.pvb_mesh_query(ctypes.byref(desc), nat.ptr(d_in), m, mode, nat.ptr(dist), nat.ptr(grad),
+                                           nat.ptr(closest), None, nat.ptr(normal), nat.ptr(ws),
+                                           ws.numel() if ws is not None else 0, nat.stream_ptr(device)),
+                          "pvb_mesh_query")
+
+            o = list(st[1].run(points_in_object_frame, launch))
+            closest = o.pop(0).reshape(*lead, 3) if want_closest else None
+            dist, grad = o.pop(0).reshape(lead), o.pop(0).reshape(*lead, 3)
+            normal = o.pop(0).reshape(*lead, 3) if compute_normal else None
+            return closest, dist, grad, normal
         with torch.cuda.device(device):
             p = nat.as_f32_points(points_in_object_frame, device)
             n = p.shape[0]
             dist = torch.empty(n, dtype=torch.float32, device=device)
             grad = torch.empty(n, 3, dtype=torch.float32, device=device)
-            closest = torch.empty(n, 3, dtype=torch.float32, device=device)
+            closest = torch.empty(n, 3, dtype=torch.float32, device=device) if want_closest else None
             normal = torch.empty(n, 3, dtype=torch.float32, device=device) if compute_normal else None
             desc = self.native_desc(device)
             face = None
-            if self.sign_mode == "winding" and (mode & nat.PVB_MESH_SIGNED):
+            if winding:
                 mode |= nat.PVB_MESH_WINDING
                 desc.wn_nodes = self._winding_state(device).data_ptr()
                 face = torch.empty(n, dtype=torch.int32, device=device)
-            elif self.sign_mode != "parity":
-                raise ValueError(f"sign_mode must be 'parity' or 'winding', got {self.sign_mode!r}")
             ws = nat.query_workspace(n, device)
-            nat.check(nat.lib().pvb_mesh_query(ctypes.byref(desc), nat.ptr(p), n, mode, nat.ptr(dist), nat.ptr(grad),
-                                               nat.ptr(closest), nat.ptr(face), nat.ptr(normal), nat.ptr(ws),
-                                               ws.numel() if ws is not None else 0, nat.stream_ptr(device)),
+            nat.check(L.pvb_mesh_query(ctypes.byref(desc), nat.ptr(p), n, mode, nat.ptr(dist), nat.ptr(grad),
+                                       nat.ptr(closest), nat.ptr(face), nat.ptr(normal), nat.ptr(ws),
+                                       ws.numel() if ws is not None else 0, nat.stream_ptr(device)),
                       "pvb_mesh_query")
 
         def fin(t, tail):
             return nat.deliver(t, out_device, dtype).reshape(*lead, *tail)
 
-        return (fin(closest, (3,)), fin(dist, ()), fin(grad, (3,)),
+        return (fin(closest, (3,)) if want_closest else None, fin(dist, ()), fin(grad, (3,)),
                 fin(normal, (3,)) if compute_normal else None)
 
     def object_frame_closest_point(self, points_in_object_frame, compute_normal=False) -> SDFQuery:
@@ -444,7 +544,13 @@ class MeshSDF(ObjectFrameSDF):
         return torch.tensor(self.obj_factory.bounding_box(**kwargs))
 
     def __call__(self, points_in_object_frame):
-        res = self.obj_factory.object_frame_closest_point(points_in_object_frame)
+        of = self.obj_factory
+        if (type(of).object_frame_closest_point is ObjectFactory.object_frame_closest_point
+                and type(of)._do_object_frame_closest_point is ObjectFactory._do_object_frame_closest_point):
+            # stock factory: distance and gradient only -- no closest-point output, no copy of it to a host caller
+            _, dist, grad, _ = of._do_object_frame_closest_point(points_in_object_frame, want_closest=False)
+            return dist, grad
+        res = of.object_frame_closest_point(points_in_object_frame)
         return res.distance, res.gradient
 
     def native_desc(self, device):
@@ -677,13 +783,60 @@ class ComposedSDF(ObjectFrameSDF):
             bwhich = torch.where(better, torch.full_like(bwhich, i), bwhich)
         return (best, bgrad, bwhich) if return_which else (best, bgrad)
 
+    #: host callers with at least this many result bytes get their result streamed out slab by slab
+    host_result_pipeline_min_bytes = 64 << 20
+
+    def _host_result_pipeline(self, points_in_object_frame):
+        """Host points in, pinned host results out, for results so large that the device-to-host copy IS the call
+        (C4: 0.45 ms of lookups, 5.8 ms of PCIe): the configurations are queried in slabs (a first small one, then 64 at
+        a time -- whole 32-configuration tiles) into one device buffer, and each slab starts its copy on a side stream
+        as soon as its kernel has finished, so only the first slab's lookups are not hidden behind the copy.
+        Returns None when the call does not qualify (then __call__ takes the plain path)."""
+        if not (torch.is_tensor(points_in_object_frame) and points_in_object_frame.device.type == "cpu"
+                and points_in_object_frame.dtype == torch.float32 and self.tsf_batch is not None):
+            return None
+        n_cfg = math.prod(list(self.tsf_batch))
+        P = points_in_object_frame.numel() // 3
+        if n_cfg < 64 or 16 * n_cfg * P < self.host_result_pipeline_min_bytes:
+            return None
+        device = nat.compute_device(None)
+        if self._native_descs(device)[0] is None:
+            return None
+        with torch.cuda.device(device):
+            cur = torch.cuda.current_stream(device)
+            p = nat.as_f32_points(points_in_object_frame, device)
+            val_d = torch.empty(n_cfg * P, dtype=torch.float32, device=device)
+            grad_d = torch.empty(n_cfg * P, 3, dtype=torch.float32, device=device)
+            val_h = torch.empty(n_cfg * P, dtype=torch.float32, pin_memory=True)
+            grad_h = torch.empty(n_cfg * P, 3, dtype=torch.float32, pin_memory=True)
+            s_out = getattr(self, "_s_out", None)
+            if s_out is None or s_out.device != device:
+                s_out = self._s_out = torch.cuda.Stream(device)
+            b = 0
+            while b < n_cfg:
+                c = min(32 if b == 0 else 64, n_cfg - b)
+                self.query_at(p, val_d.data_ptr(), grad_d.data_ptr(), b, c)
+                done = torch.cuda.Event()
+                done.record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(done)
+                    val_h[b * P:(b + c) * P].copy_(val_d[b * P:(b + c) * P], non_blocking=True)
+                    grad_h[b * P:(b + c) * P].copy_(grad_d[b * P:(b + c) * P], non_blocking=True)
+                b += c
+            s_out.synchronize()        # the device buffers may be recycled from here on
+        return val_h, grad_h
+
     def __call__(self, points_in_object_frame):
         pts_shape = tuple(points_in_object_frame.shape)
-        vv, gg = self.query(points_in_object_frame)
-        dtype = points_in_object_frame.dtype if torch.is_tensor(points_in_object_frame) else torch.float
-        out_device = points_in_object_frame.device if torch.is_tensor(points_in_object_frame) else "cpu"
-        vv = nat.deliver(vv, out_device, dtype)
-        gg = nat.deliver(gg, out_device, dtype)
+        piped = self._host_result_pipeline(points_in_object_frame)
+        if piped is not None:
+            vv, gg = piped
+        else:
+            vv, gg = self.query(points_in_object_frame)
+            dtype = points_in_object_frame.dtype if torch.is_tensor(points_in_object_frame) else torch.float
+            out_device = points_in_object_frame.device if torch.is_tensor(points_in_object_frame) else "cpu"
+            vv = nat.deliver(vv, out_device, dtype)
+            gg = nat.deliver(gg, out_device, dtype)
         if self.tsf_batch is not None:
             # configuration batch dims first, then the query points' batch dims (sdf.py:428-431)
             vv = vv.reshape(*self.tsf_batch, *pts_shape[:-1])
@@ -941,68 +1094,24 @@ class CachedSDF(ObjectFrameSDF):
                                             nat.stream_ptr(device)), "pvb_grid_lookup")
         return p, val, grad, outside, index
 
-    #: host batches at least this large are streamed through the GPU in chunks (copy-in / lookup / copy-out
-    #: overlapped on three streams); smaller ones take one H2D copy, one launch, one D2H copy
-    #: (measured on the pool, 1e7 points: plain 5.1 ms, 2M-point chunks 3.7 ms, 4M 4.1 ms, 1M 11 ms -- small chunks
-    #: are dominated by per-chunk stream/event bookkeeping on this host)
+    #: host batches at least this large are streamed through the GPU in chunks (_HostChunkStream: copy-in / lookup /
+    #: copy-out overlapped on three streams); smaller ones take one H2D copy, one launch, one D2H copy
     host_pipeline_min_points = 1 << 22
     host_pipeline_chunk = 1 << 21
 
     def _host_pipeline(self, points):
-        """Host tensor in, pinned host tensors out, PCIe busy in both directions at once.
-
-        Chunk i is copied in on `s_in` while chunk i-1 is looked up on the current stream and chunk i-2 is copied
-        out on `s_out`; two device slots per direction, events order the reuse of a slot."""
+        """Host tensor in, pinned host (values, gradients) out through the chunk pipeline."""
         device = self._cdev
-        src = points.detach().reshape(-1, 3)
-        if src.dtype != torch.float32:
-            src = src.float()
-        src = src.contiguous()
-        n = src.shape[0]
-        C = self.host_pipeline_chunk
-        with torch.cuda.device(device):
-            cur = torch.cuda.current_stream(device)
-            st = getattr(self, "_pipe_state", None)
-            if st is None:
-                st = {"s_in": torch.cuda.Stream(device), "s_out": torch.cuda.Stream(device),
-                      "d_in": [torch.empty(C, 3, dtype=torch.float32, device=device) for _ in range(2)],
-                      "d_val": [torch.empty(C, dtype=torch.float32, device=device) for _ in range(2)],
-                      "d_grad": [torch.empty(C, 3, dtype=torch.float32, device=device) for _ in range(2)]}
-                self._pipe_state = st
-            s_in, s_out = st["s_in"], st["s_out"]
-            val_h = torch.empty(n, dtype=torch.float32, pin_memory=True)
-            grad_h = torch.empty(n, 3, dtype=torch.float32, pin_memory=True)
-            L = nat.lib()
-            s_in.wait_stream(cur)
-            s_out.wait_stream(cur)
-            ev_comp = [None, None]      # lookup finished reading d_in[b] / writing d_val[b]
-            ev_out = [None, None]       # copy-out finished reading d_val[b]
-            for i, lo in enumerate(range(0, n, C)):
-                hi = min(lo + C, n)
-                m = hi - lo
-                b = i & 1
-                with torch.cuda.stream(s_in):
-                    if ev_comp[b] is not None:
-                        s_in.wait_event(ev_comp[b])
-                    st["d_in"][b][:m].copy_(src[lo:hi], non_blocking=True)
-                    ev_in = torch.cuda.Event()
-                    ev_in.record(s_in)
-                cur.wait_event(ev_in)
-                if ev_out[b] is not None:
-                    cur.wait_event(ev_out[b])
-                nat.check(L.pvb_grid_lookup(ctypes.byref(self._desc), nat.ptr(st["d_in"][b]), m,
-                                            nat.ptr(st["d_val"][b]), nat.ptr(st["d_grad"][b]), None, 0.0, None,
-                                            nat.stream_ptr(device)), "pvb_grid_lookup")
-                ev_comp[b] = torch.cuda.Event()
-                ev_comp[b].record(cur)
-                with torch.cuda.stream(s_out):
-                    s_out.wait_event(ev_comp[b])
-                    val_h[lo:hi].copy_(st["d_val"][b][:m], non_blocking=True)
-                    grad_h[lo:hi].copy_(st["d_grad"][b][:m], non_blocking=True)
-                    ev_out[b] = torch.cuda.Event()
-                    ev_out[b].record(s_out)
-            s_out.synchronize()
-            cur.wait_stream(s_in)
+        st = getattr(self, "_pipe_state", None)
+        if st is None or st.chunk != self.host_pipeline_chunk or st.device != device:
+            st = self._pipe_state = _HostChunkStream(device, self.host_pipeline_chunk, ((), (3,)))
+        L = nat.lib()
+
+        def launch(d_in, m, d_out):
+            nat.check(L.pvb_grid_lookup(ctypes.byref(self._desc), nat.ptr(d_in), m, nat.ptr(d_out[0]), nat.ptr(d_out[1]),
+                                        None, 0.0, None, nat.stream_ptr(device)), "pvb_grid_lookup")
+
+        val_h, grad_h = st.run(points, launch)
         return val_h, grad_h
 
     def __call__(self, points_in_object_frame):

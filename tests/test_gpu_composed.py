@@ -326,3 +326,31 @@ def test_robot_kernel_equals_point_major_and_ragged(tmp_path):
             v1, g1, w1 = s.sdf.query(pts, cfg_begin=i, cfg_count=1, return_which=True)     # point-major kernel
             sl = slice(i * n_pts, (i + 1) * n_pts)
             assert torch.equal(v1, v[sl]) and torch.equal(g1, g[sl]) and torch.equal(w1, w[sl]), (n_cfg, n_pts, i)
+
+
+@pytest.mark.gpu
+def test_host_result_pipeline_equals_plain_path(tmp_path):
+    """ComposedSDF.__call__ with host points and a result above `host_result_pipeline_min_bytes` streams the result
+    out slab by slab (32 configurations, then 64 at a time, copies on a side stream): bit-identical to the plain path,
+    same shapes, pinned host tensors; non-qualifying calls (small result, fp64 points) keep the plain path."""
+    import pytorch_volumetric_b200 as pv
+    urdf, end = workloads.write_arm(str(tmp_path))
+    chain = pv.build_serial_chain_from_urdf(open(urdf).read(), end).to(device="cuda")
+    s = pv.RobotSDF(chain, path_prefix=str(tmp_path),
+                    link_sdf_cls=pv.cache_link_sdf_factory(resolution=0.02, padding=1.0, device="cuda",
+                                                           cache_path=str(tmp_path / "arm.pkl")))
+    lo = [r[0] for r in workloads.ARM_QUERY_RANGE]; hi = [r[1] for r in workloads.ARM_QUERY_RANGE]
+    pts = workloads.uniform_points(3001, lo, hi, seed=11)
+    for n_cfg in (64, 135):                   # 32 + 32, 32 + 64 + 39
+        s.set_joint_configuration(workloads.arm_configurations(n_cfg).cuda())
+        v0, g0 = s(pts)                        # 16 * 135 * 3001 bytes < 64 MiB: plain path
+        assert s.sdf._host_result_pipeline(pts) is None
+        s.sdf.host_result_pipeline_min_bytes = 1 << 20
+        try:
+            assert s.sdf._host_result_pipeline(pts.double()) is None
+            v1, g1 = s(pts)
+        finally:
+            del s.sdf.host_result_pipeline_min_bytes
+        assert v1.device.type == "cpu" and v1.is_pinned() and v1.shape == (n_cfg, 3001) and g1.shape == (n_cfg, 3001, 3)
+        assert torch.equal(v0, v1) and torch.equal(g0, g1)
+

@@ -97,6 +97,35 @@ def test_batched_shapes_and_host_inputs():
     assert v0.shape == (0,) and g0.shape == (0, 3)
 
 
+def test_host_chunk_pipeline_equals_plain_path():
+    """Large host batches are streamed through the GPU in chunks (copy-in / walk / copy-out on three streams): the same
+    bits as one copy + one launch, for MeshSDF.__call__ (distance + gradient only) and for the full SDFQuery incl. the
+    normal; the tail chunk is ragged, and a chunk size above the batch is a single chunk."""
+    import pytorch_volumetric_b200 as pv
+    v, f = workloads.bumpy_sphere(40, 21)
+    obj = pv.MeshObjectFactory("bumpy", mesh=(v, f))
+    assert obj.is_closed
+    sdf = pv.MeshSDF(obj)
+    pts = workloads.uniform_points(10_001, v.min(0) - 0.05, v.max(0) + 0.05, seed=5)
+    v0, g0 = sdf(pts)
+    q0 = obj.object_frame_closest_point(pts, compute_normal=True)
+    assert getattr(obj, "_pipe_state", None) is None
+    try:
+        obj.host_pipeline_min_points = 1000
+        for chunk in (2048, 1 << 15):
+            obj.host_pipeline_chunk = chunk
+            v1, g1 = sdf(pts)
+            assert v1.is_pinned() and v1.shape == (10_001,) and g1.shape == (10_001, 3)
+            assert torch.equal(v0, v1) and torch.equal(g0, g1)
+            q1 = obj.object_frame_closest_point(pts.view(1, 10_001, 3), compute_normal=True)
+            assert q1.closest.shape == (1, 10_001, 3) and q1.distance.shape == (1, 10_001)
+            for a, b in zip(q0, q1):
+                assert torch.equal(a, b.reshape(a.shape))
+        assert obj._pipe_state is not None
+    finally:
+        del obj.host_pipeline_min_points, obj.host_pipeline_chunk
+
+
 def test_mesh_query_large_properties():
     """North-star size (10^7 queries on the 10k-triangle mesh) through size-independent properties:
     closest point lies on the surface (its own distance is ~0), |grad| = 1, sign matches the radial test of a
