@@ -171,7 +171,6 @@ __device__ __forceinline__ f3 load_point(const float *__restrict__ pts, long lon
 // (histogram by atomics, single-block scan, scatter) and the tree walk processes them in that order through an
 // index permutation; results are written to the original slots, so callers see no reordering.
 constexpr int kSortBits = 6;                               // per axis: 64^3 cells (default)
-constexpr int kSortCells = 1 << (3 * kSortBits);           // 262144
 constexpr int kSortBitsMax = 8;                            // 256^3 cells = 64 MB of counters
 
 // Cells per axis for a batch of n queries.  Lanes of a warp are 32 consecutive queries of the binned order: they walk
@@ -230,7 +229,7 @@ __global__ void sort_hist_kernel(const SortFrame f, const float *__restrict__ pt
     }
 }
 
-// exclusive scan of kSortCells counters in place, one block of 1024 threads (256 counters per thread, moved as
+// exclusive scan of the cell counters in place, one block of 1024 threads (256 counters per thread, moved as
 // 64 independent 128-bit loads so that the single block is not serialised on L2 latency: 442 us -> tens of us)
 __global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t *__restrict__ hist, int n_cells) {
     __shared__ uint32_t warp_sum[32];
@@ -911,7 +910,7 @@ composed_cfgmajor_kernel(const __grid_constant__ DescPack<kCmMaxS> descs, int n_
                          int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, long long n_pts,
                          float *__restrict__ out_val, float *__restrict__ out_grad, int *__restrict__ out_which,
                          const __grid_constant__ OutTargets tg) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     CmSmem &sm = *reinterpret_cast<CmSmem *>(smem_raw);
     NodeStage st; st.smem = nullptr; st.n = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1143,7 +1142,7 @@ robot_query_kernel(const __grid_constant__ RobotPack<MAXS> pk, int n_sdf, const 
                    int cfg_begin, int cfg_count, const float *__restrict__ pts, int n_pts, int vec,
                    float *__restrict__ out_val, float *__restrict__ out_grad, int *__restrict__ out_which,
                    const __grid_constant__ OutTargets tg) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     RobotSmem<MAXS> &sm = *reinterpret_cast<RobotSmem<MAXS> *>(smem_raw);
     NodeStage st; st.smem = nullptr; st.n = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1443,7 +1442,7 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
                     int n_cfg, int cfg_begin, int cfg_count, const float *__restrict__ pts, int n_pts, int vec,
                     int chunk_log2, float *__restrict__ out_val, float *__restrict__ out_grad,
                     int *__restrict__ out_which, const __grid_constant__ OutTargets tg) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int c0, lc_log2;
