@@ -46,3 +46,20 @@ def test_reference_arm_other_ranks_exit_quietly():
                           "--warmup", "0", "--gpus", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                          timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_committed_ncu_side_files_cover_every_workload():
+    """roofline.traffic / roofline.ncu are read from committed ncu extracts: every bench workload has an entry, the
+    summaries they cite exist, and the numbers are sane (bytes > 0, percentages in (0, 100])."""
+    sys.path.insert(0, ROOT)
+    import bench
+    names = {bench.HEADLINE, *bench.OTHER_WORKLOADS}
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    limits = json.load(open(os.path.join(ROOT, "profiles", "ncu_limits.json")))
+    assert names <= set(traffic) and names <= set(limits)
+    for n in names:
+        assert traffic[n] > 0 and bench.ncu_traffic(n) == traffic[n]
+        lim = bench.ncu_limits(n)
+        assert os.path.exists(os.path.join(ROOT, lim["source"])), lim["source"]
+        for k in ("issue_slots_pct", "l1_data_pipe_pct", "dram_pct", "warps_active_pct"):
+            assert 0.0 < lim[k] <= 100.0, (n, k, lim[k])
