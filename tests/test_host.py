@@ -433,3 +433,13 @@ def test_cpulist_parser_and_numa_binding_is_a_noop_without_gpu():
     assert pd.bind_to_gpu_numa_node(0) is None
     if before is not None:
         assert os.sched_getaffinity(0) == before
+
+
+def test_every_declared_symbol_is_documented_in_integration_md():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "pvb.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(pvb_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 31
+    missing = [n for n in names if n not in doc]
+    assert not missing, missing
