@@ -1399,7 +1399,10 @@ robot_query_kernel(const __grid_constant__ RobotPack<MAXS> pk, int n_sdf, const 
 // it now: L1 data-pipe wavefronts at 78 % (~166 per point: 32 sphere reads, ~54 transform rows, ~66 table gathers of 32
 // distinct sectors, 12 staging) with the issue slots at 70 %.
 constexpr int kRsWarps = 8;
-constexpr int kRsChunk = 8;                       // consecutive points per warp between two flushes
+#ifndef PVB_RS_CHUNK
+#define PVB_RS_CHUNK 8
+#endif
+constexpr int kRsChunk = PVB_RS_CHUNK;            // consecutive points per warp between two flushes (8, or 4: tuning builds)
 constexpr int kRsMaxS = 8;
 constexpr int kRsValStride = kRsChunk + 1;        // 9: conflict-free STS.32 across lanes
 constexpr int kRsGradStride = 3 * kRsChunk + 1;   // 25
@@ -1407,6 +1410,10 @@ constexpr int kRsGradStride = 3 * kRsChunk + 1;   // 25
 // (The lane's 8 bounding spheres kept in 32 registers instead of shared memory -- no LDS in the bound pass, but 80
 // registers / 3 CTAs per SM -- measured 0.70 ms against 0.56 ms for the shared-memory form on C4; 48 registers / 5 CTAs
 // with spills 0.70 ms; 80 registers without spills 0.60 ms: profiles/r02/tune_c4_serial_variants.jsonl.)
+// (More than 4 blocks per SM needs <= 48 registers AND <= 45 KB of shared memory per block, i.e. 4-point staging tiles
+// (PVB_RS_CHUNK=4: 35.8 KB).  Measured on C4, kernel only: 4 blocks 0.472 ms (8-point tiles 0.455), 5 blocks / 48
+// registers 0.533, 6 blocks / 40 registers 0.600 -- the spills go through the L1 data pipe that already bounds the
+// kernel.  profiles/r02/tune_c4_occupancy.jsonl)
 #ifndef PVB_RS_MINB
 #define PVB_RS_MINB 4
 #endif
@@ -2356,7 +2363,7 @@ static int launch_robot_serial(const pvb_sdf_desc *descs, int n_sdf, const float
     // 0.497 / 0.517 -- profiles/r02/tune_c4_fine_steps.jsonl)
     static const int fine_below = [] { const char *e = getenv("PVB_ROBOT_FINE_STEPS"); return e ? atoi(e) : 12; }();
     const long long slots = (long long)sm_count() * PVB_RS_MINB * kRsWarps;
-    const int chunk_log2 = (total_steps < (long long)fine_below * slots) ? 2 : 3;
+    const int chunk_log2 = (kRsChunk == 4 || total_steps < (long long)fine_below * slots) ? 2 : 3;
     const long long n_chunks = (n_pts + (1 << chunk_log2) - 1) >> chunk_log2;     // steps of a 32-configuration tile
     static const int waves = [] { const char *e = getenv("PVB_ROBOT_WAVES"); return e ? atoi(e) : 4; }();
     long long gx = ((long long)sm_count() * PVB_RS_MINB * waves + gy - 1) / gy;
