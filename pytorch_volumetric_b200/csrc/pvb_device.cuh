@@ -657,4 +657,39 @@ __device__ __forceinline__ void rs_flush_piece(int c, int chunk_log2, int sub_lo
     part = is_val ? g & ((1 << vper_log2) - 1) : g - ((3 * row) << vper_log2);
 }
 
+// The first visit of a point goes to the link whose bounding sphere gives the smallest lower bound.  Instead of a
+// compare + two selects per link, every bound becomes a key that carries its link index in the 3 low mantissa bits --
+// (bits & ~7) | si, ONE LOP3 in the device build with ~7 in a register the compiler cannot fold -- and the smallest key
+// of 8 (5 FMNMX) names the link.  A bound of -inf (not valid: never rejected) or +inf (slot beyond n_sdf) turns into a
+// NaN pattern for si > 0, which fminf drops; the result is clamped to a real link.  Any link is a valid first visit --
+// the visiting order never changes a result -- so the 7-ulp blur of the keys is harmless (tests/test_hostsim.py).
+__device__ __forceinline__ int rs_and_or(int a, int b, int c) {
+#ifdef __CUDA_ARCH__
+    int r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return (a & b) | c;
+#endif
+}
+
+__device__ __forceinline__ float rs_bound_key(float lb, int low3_off, int si) {
+    return __int_as_float(rs_and_or(__float_as_int(lb), low3_off, si));
+}
+
+__device__ __forceinline__ float rs_min(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return fminf(a, b);             // FMNMX: a NaN operand loses, signalling or not
+#else
+    return a != a ? b : (b != b ? a : (a < b ? a : b));     // (glibc's fminf turns a signalling NaN into a quiet one)
+#endif
+}
+
+__device__ __forceinline__ int rs_nearest(const float (&key)[8], int n_sdf) {
+    const float kmin = rs_min(rs_min(rs_min(key[0], key[1]), rs_min(key[2], key[3])),
+                              rs_min(rs_min(key[4], key[5]), rs_min(key[6], key[7])));
+    const int si = __float_as_int(kmin) & 7;
+    return si < n_sdf - 1 ? si : n_sdf - 1;
+}
+
 }  // namespace pvb

@@ -1430,12 +1430,6 @@ struct __align__(16) RsSmem {
 // approximate reciprocal square root (2 ulp) and the roundings of the three fused multiply-adds
 constexpr float kRsBoundScale = 0.99989899f;
 
-__device__ __forceinline__ int and_or(int a, int b, int c) {   // (a & b) | c
-    int r;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-}
-
 __device__ __forceinline__ float rsqrt_approx(float x) {      // one MUFU.RSQ, no denormal fix-up (callers keep x >= 1e-20)
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -1546,16 +1540,11 @@ robot_serial_kernel(const __grid_constant__ RobotPack<kRsMaxS> pk, int n_sdf, co
                 const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
                 const float d2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, 1e-20f)));
                 lb[si] = fmaf(d2 * rsqrt_approx(d2), kRsBoundScale, -sp.w);
-                // the link index rides in the 3 low mantissa bits: the smallest key names the nearest sphere
-                key[si] = __int_as_float(and_or(__float_as_int(lb[si]), low3_off, si));
+                key[si] = rs_bound_key(lb[si], low3_off, si);       // link index in the 3 low mantissa bits
             }
-            // one visiting order per point group: its first lane's nearest sphere (neighbouring configurations agree).
-            // Any link is a valid first visit -- the order never changes a result -- so the 7-ulp blur of the keys and
-            // fminf dropping the NaN patterns that +-inf bounds turn into do no harm; the clamp keeps it a real link.
-            const float kmin = fminf(fminf(fminf(key[0], key[1]), fminf(key[2], key[3])),
-                                     fminf(fminf(key[4], key[5]), fminf(key[6], key[7])));
-            int pred = min(__float_as_int(kmin) & 7, n_sdf - 1);
-            pred = __shfl_sync(0xffffffffu, pred, sub << lc_log2);
+            // one visiting order per point group: its first lane's nearest sphere (neighbouring configurations agree;
+            // rs_nearest in pvb_device.cuh: any link is a valid first visit, the order never changes a result)
+            const int pred = __shfl_sync(0xffffffffu, rs_nearest(key, n_sdf), sub << lc_log2);
             float best = PVB_INF;
             f3 bg = mk3(0.f, 0.f, 0.f);
             int bs = -1;

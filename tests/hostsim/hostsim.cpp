@@ -122,6 +122,15 @@ extern "C" void sim_rs_flush_piece(int c, int chunk_log2, int sub_log2, int w_lo
     *is_val = v ? 1 : 0;
 }
 
+// nearest-sphere selection of robot_serial_kernel: bounds -> keys -> smallest key -> link index (n rows of 8 bounds)
+extern "C" void sim_rs_nearest(const float *lb, long long n, int n_sdf, int *pred) {
+    for (long long i = 0; i < n; ++i) {
+        float key[8];
+        for (int si = 0; si < 8; ++si) key[si] = rs_bound_key(lb[8 * i + si], ~7, si);
+        pred[i] = rs_nearest(key, n_sdf);
+    }
+}
+
 // closest-point walk with a per-query initial search radius (squared): how many node visits / triangle tests are
 // irreducible once the answer is known (scripts/traversal_stats.py, the lower bound any seeding scheme could reach)
 extern "C" void sim_closest_seeded(const pvb_sdf_desc *m, const float *pts, long long n, const float *init_d2,

@@ -354,3 +354,33 @@ def test_host_result_pipeline_equals_plain_path(tmp_path):
         assert v1.device.type == "cpu" and v1.is_pinned() and v1.shape == (n_cfg, 3001) and g1.shape == (n_cfg, 3001, 3)
         assert torch.equal(v0, v1) and torch.equal(g0, g1)
 
+
+@pytest.mark.gpu
+def test_robot_kernel_with_nonrigid_transforms(tmp_path):
+    """robot_serial_kernel's bounding-sphere bounds need isometries: (configuration, link) transforms that are not
+    (scaled rotation blocks here) get no sphere bound at all -- their keys are NaN patterns in the nearest-sphere
+    selection -- and must still produce what the point-major kernel (no sphere bounds) produces, bit for bit."""
+    import pytorch_volumetric_b200 as pv
+    from pytorch_volumetric_b200.transforms import matrix_of
+    urdf, end = workloads.write_arm(str(tmp_path))
+    chain = pv.build_serial_chain_from_urdf(open(urdf).read(), end).to(device="cuda")
+    s = pv.RobotSDF(chain, path_prefix=str(tmp_path),
+                    link_sdf_cls=pv.cache_link_sdf_factory(resolution=0.02, padding=1.0, device="cuda",
+                                                           cache_path=str(tmp_path / "arm.pkl")))
+    n_cfg, n_pts = 40, 4096
+    s.set_joint_configuration(workloads.arm_configurations(n_cfg).cuda())
+    S = len(s.sdf.sdfs)
+    M = matrix_of(s.sdf.obj_frame_to_link_frame).detach().clone().reshape(S, n_cfg, 4, 4)
+    M[:, 5:13, :3, :3] *= 1.03              # every link of configurations 5..12
+    M[3, 20:26, :3, :3] *= 0.97             # one link of configurations 20..25
+    M[0, 30:, :3, :3] *= 1.02               # link 0 (the slot whose -inf bound stays a valid float key)
+    comp = pv.ComposedSDF(s.sdf.sdfs, pv.Transform3d(matrix=M.reshape(S * n_cfg, 4, 4)))
+    assert tuple(comp.tsf_batch) == (n_cfg,)
+    lo = [r[0] for r in workloads.ARM_QUERY_RANGE]; hi = [r[1] for r in workloads.ARM_QUERY_RANGE]
+    pts = workloads.uniform_points(n_pts, lo, hi, seed=13).cuda()
+    v, g, w = comp.query(pts, return_which=True)
+    for i in (0, 5, 12, 22, 31, 39):
+        v1, g1, w1 = comp.query(pts, cfg_begin=i, cfg_count=1, return_which=True)
+        sl = slice(i * n_pts, (i + 1) * n_pts)
+        assert torch.equal(v1, v[sl]) and torch.equal(g1, g[sl]) and torch.equal(w1, w[sl]), i
+

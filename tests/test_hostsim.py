@@ -423,3 +423,38 @@ def test_robot_serial_tiles_and_flush_pieces_cover_everything_once(built_lib):
                         assert cur[2] == prev[2] + 1            # consecutive pieces are neighbours in the row
                     prev = cur
                 assert (val == 1).all() and (grad == 1).all(), (w_log2, chunk_log2, sub_log2)
+
+
+def test_robot_serial_nearest_sphere_key(built_lib):
+    """rs_bound_key / rs_nearest (pvb_device.cuh): the link index rides in the 3 low mantissa bits of each sphere bound
+    and the smallest key names the first link to visit.  Always a real link (0 <= pred < n_sdf), whatever mix of finite,
+    -inf (bound not valid) and +inf (slot beyond n_sdf) bounds comes in; the argmin whenever the smallest finite bound
+    is separated from the rest by more than the 7-ulp blur of the keys; -inf at slot 0 wins (it is a valid float)."""
+    import ctypes
+    L = hs.lib()
+    rng = np.random.default_rng(7)
+    n = 200_000
+    for n_sdf in range(1, 9):
+        lb = rng.normal(0.0, 0.3, size=(n, 8)).astype(np.float32)
+        lb[rng.random((n, 8)) < 0.05] = -np.inf                      # bounds that are not valid
+        lb[:n // 4] = np.abs(lb[:n // 4])                            # all-positive rows
+        lb[n // 4:n // 2] = -np.abs(lb[n // 4:n // 2])               # all-negative rows
+        lb[:, n_sdf:] = np.inf                                       # slots beyond n_sdf
+        lb[:16] = -np.inf; lb[:16, n_sdf:] = np.inf                  # nothing valid at all
+        pred = np.empty(n, np.int32)
+        L.sim_rs_nearest(lb.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(n), n_sdf,
+                         pred.ctypes.data_as(ctypes.c_void_p))
+        assert pred.min() >= 0 and pred.max() < n_sdf
+        valid = lb[:, :n_sdf].copy()
+        fin = np.isfinite(valid)
+        rows = fin.all(axis=1)
+        v = np.where(fin, valid, np.inf)
+        order = np.sort(v, axis=1)
+        with np.errstate(invalid="ignore"):
+            gap = order[:, 1] - order[:, 0] if n_sdf > 1 else np.full(n, np.inf, np.float32)
+        clear = rows & (gap > 16 * np.spacing(np.abs(order[:, 0]).astype(np.float32)))
+        assert clear.sum() > n // 3
+        assert np.array_equal(pred[clear], np.argmin(v, axis=1)[clear])
+        neg0 = np.isneginf(lb[:, 0])
+        assert (pred[neg0] == 0).all()
+
